@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Drop-in for the reference's src/dap_to_bed.py on the B200 device path.
+
+Same argv (src/dap_to_bed.py:139-149), same validation (:151-171), BED payload
+on stdout and nothing else (index.sh:93,102 redirect stdout into the .bed).
+
+    python -m memo_b200.dap_to_bed --mem [--order] --overlap --fai P.fai --dap dap.txt > out.bed
+"""
+import argparse
+import os
+import sys
+
+
+def parse_arguments(argv=None):
+    ap = argparse.ArgumentParser(description="Takes in .fai and full document array profile and "
+                                 "converts to bed-style MEM intervals to stdout (B200 device path).")
+    ap.add_argument("--fai", dest="fai_path", required=True, help="path to fai file")
+    ap.add_argument("--dap", dest="dap_path", required=True, help="path to full document profile")
+    ap.add_argument("--ms", dest="print_ms", action="store_true", default=False,
+                    help="Extract matching statistics (either MSs or MEMs, not both).")
+    ap.add_argument("--mem", dest="print_mems", action="store_true", default=False,
+                    help="Extract MEMs (either MSs or MEMs, not both).")
+    ap.add_argument("--overlap", dest="print_overlaps", action="store_true", default=False,
+                    help="extract overlap MEMs (only with --mem).")
+    ap.add_argument("--order", dest="sort_lcps", action="store_true", default=False,
+                    help="sort LCP row to extract order MS/MEMs.")
+    return ap.parse_args(argv)
+
+
+def check_args(args):
+    if not os.path.isfile(args.fai_path):
+        raise Exception("The fai file does not exist.")
+    if not os.path.isfile(args.dap_path):
+        raise Exception("The dap file does not exist.")
+    if not args.fai_path.endswith(".fai"):
+        raise Exception("The fai file has the incorrect file extension.")
+    if (args.print_ms + args.print_mems) != 1:
+        raise Exception("Error: Either print MSs or MEMs, not both.")
+    if args.print_overlaps and args.print_ms:
+        raise Exception("Error: Can only print overlaps if printing MEMs.")
+
+
+def main(args, sink=None):
+    from . import api, host, io
+    if args.print_ms:
+        # dead code in the reference too (NameError at src/dap_to_bed.py:51)
+        raise NotImplementedError("--ms is not on the device path (broken in the reference as well)")
+    if not args.print_overlaps:
+        raise NotImplementedError("only `--mem --overlap` (what `memo index` runs) is on the device path")
+    records = api.parse_fai(args.fai_path)
+    pos0, dap = io.read_dap_text(args.dap_path)
+    if dap.shape[0] == 0:
+        raise KeyError(None)          # reference: fai_dict[None] after an empty DAP
+    rec, start, end, col = host.build_index(dap, records, args.sort_lcps, pos_first=pos0)
+    io.write_bed(io.index_table(records, rec, start, end, col), sink)
+
+
+if __name__ == "__main__":
+    _args = parse_arguments()
+    check_args(_args)
+    main(_args)
+    sys.stdout.flush()

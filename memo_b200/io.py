@@ -1,0 +1,80 @@
+"""Host-side file formats of the hot path: dap.txt ingest, BED / Parquet index
+writers and readers.  Format conversion only -- no index arithmetic here."""
+from __future__ import annotations
+
+import sys
+from typing import Sequence, Tuple
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pyarrow.csv as pacsv
+import pyarrow.dataset as pads
+import pyarrow.parquet as pq
+
+from ._lib import MemoError
+
+INDEX_SCHEMA = pa.schema([("f0", pa.utf8()), ("f1", pa.int64()), ("f2", pa.int64()), ("f3", pa.int64())])
+
+
+def read_dap_text(path) -> Tuple[int, np.ndarray]:
+    """dap.txt (index.sh:83: `pos v1 ... vC`, single spaces) -> (first position,
+    int32 [L, C] matrix).  The device path needs consecutive positions (what
+    `nl -v0` produces); anything else is rejected loudly."""
+    table = pacsv.read_csv(
+        path,
+        read_options=pacsv.ReadOptions(autogenerate_column_names=True),
+        parse_options=pacsv.ParseOptions(delimiter=" "),
+    )
+    if table.num_columns < 2:
+        raise MemoError("dap.txt needs a position column and at least one genome column")
+    for i, col in enumerate(table.columns):
+        if not pa.types.is_integer(col.type):
+            raise ValueError(f"invalid literal for int() in DAP column {i}")     # int() in the reference
+    L = table.num_rows
+    if L == 0:
+        return 0, np.zeros((0, table.num_columns - 1), dtype=np.int32)
+    pos = table.column(0).to_numpy()
+    if L > 1 and not (np.diff(pos) == 1).all():
+        raise MemoError("dap.txt positions are not consecutive (expected `nl -v0` numbering)")
+    C = table.num_columns - 1
+    out = np.empty((L, C), dtype=np.int32)
+    for j in range(C):
+        col = table.column(j + 1)
+        mm = pc.min_max(col).as_py()
+        if mm["min"] < 0 or mm["max"] > 2**31 - 1:
+            raise MemoError("DAP lengths must be in [0, 2^31)")
+        out[:, j] = col.to_numpy()
+    return int(pos[0]), out
+
+
+def index_table(records: Sequence[Tuple[str, int]], rec_idx, start, end, order) -> pa.Table:
+    """Arrow table with the index schema (f0 string, f1..f3 int64), f0
+    dictionary-free so that it equals what parquet_compress_bed.py reads back."""
+    names = pa.array([r[0] for r in records], type=pa.utf8())
+    f0 = pc.take(names, pa.array(np.asarray(rec_idx, dtype=np.int64)))
+    return pa.table([f0, pa.array(np.asarray(start, dtype=np.int64)),
+                     pa.array(np.asarray(end, dtype=np.int64)),
+                     pa.array(np.asarray(order, dtype=np.int64))], schema=INDEX_SCHEMA)
+
+
+def write_bed(table: pa.Table, sink=None) -> None:
+    """BED payload as dap_to_bed.py prints it: tab separated, no header."""
+    sink = sys.stdout.buffer if sink is None else sink
+    if table.num_rows == 0:
+        return
+    pacsv.write_csv(table, sink, write_options=pacsv.WriteOptions(
+        include_header=False, delimiter="\t", quoting_style="none"))
+
+
+def write_parquet(table: pa.Table, path, codec: str = "ZSTD") -> None:
+    pq.write_table(table, path, compression=codec)
+
+
+def read_index_rows(path, record: str, f1_gt: int, f1_lt: int):
+    """Index rows of `record` with f1_gt < f1 < f1_lt (the live predicate of
+    memo_query.py:25-27; the other predicate's rows can never paint)."""
+    dataset = pads.dataset(path, format="parquet")
+    flt = (pads.field("f0") == record) & (pads.field("f1") > f1_gt) & (pads.field("f1") < f1_lt)
+    t = dataset.to_table(filter=flt, columns=["f1", "f2", "f3"])
+    return (t.column("f1").to_numpy(), t.column("f2").to_numpy(), t.column("f3").to_numpy())

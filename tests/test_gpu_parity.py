@@ -1,0 +1,222 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the
+reference-generated golden fixtures.  Bit-exact: everything here is integer."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import memo_oracle as mo  # noqa: E402  (checker only)
+
+
+def _api():
+    from memo_b200 import api
+    return api
+
+
+def gpu_index(vals, records, order, **kw):
+    api = _api()
+    dap = torch.from_numpy(np.ascontiguousarray(vals, dtype=np.int32)).cuda()
+    res = api.index_build(dap, records, order, **kw)
+    return res, res.to_host()
+
+
+def assert_index_equal(got, want, ctx=""):
+    names = ("rec", "start", "end", "col")
+    for g, w, n in zip(got, want, names):
+        assert g.shape == w.shape, f"{ctx}: {n} count {g.shape} != {w.shape}"
+        if not np.array_equal(g, w):
+            i = int(np.flatnonzero(g != w)[0])
+            raise AssertionError(f"{ctx}: {n} differs first at row {i}: got {g[i]} want {w[i]}")
+
+
+def gpu_query(s, e, c, qs, qe, k, n_docs, membership):
+    api = _api()
+    f1 = torch.from_numpy(s.astype(np.int32)).cuda()
+    f2 = torch.from_numpy(e.astype(np.uint32).view(np.int32)).cuda()
+    f3 = torch.from_numpy(c.astype(np.int32)).cuda()
+    if membership:
+        bits = api.query_membership(f1, f2, f3, qs, qe, k, n_docs)
+        return api.unpack_membership(bits.cpu().numpy(), n_docs), bits
+    out = api.query_conservation(f1, f2, f3, qs, qe, k, n_docs)
+    return out.cpu().numpy().astype(np.int64), out
+
+
+# ------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("order", [True, False])
+def test_example_index_golden(example_golden, order):
+    g = example_golden
+    res, got = gpu_index(g["vals"], g["records"], order)
+    assert mo.format_bed(g["records"], *got) == (g["cons_bed"] if order else g["memb_bed"])
+    assert not res.irregular
+
+
+def test_example_queries_golden(example_golden):
+    api = _api()
+    g = example_golden
+    for q in g["queries"]:
+        bed = g["memb_bed"] if q["membership"] else g["cons_bed"]
+        arr = np.array([[int(x) for x in l.split("\t")[1:]] for l in bed.splitlines()], dtype=np.int64)
+        chrom, se = q["region"].split(":")
+        s, e = map(int, se.split("-"))
+        if chrom != "ref_1":
+            arr = arr[:0]
+        out, dev = gpu_query(arr[:, 0], arr[:, 1], arr[:, 2], s, e, q["k"], q["n"], q["membership"])
+        if q["membership"]:
+            assert api.format_membership(dev, q["n"]).decode() == q["out"], q
+        else:
+            assert api.format_conservation(dev).decode() == q["out"], q
+
+
+def test_fuzz_goldens(fuzz_golden):
+    arrays, meta = fuzz_golden
+    n_general = 0
+    for case in meta:
+        name = case["name"]
+        recs = [tuple(r) for r in case["records"]]
+        vals = arrays[f"{name}.vals"]
+        hdrs = [h for h, _ in recs]
+        for order, tag in ((True, "cons"), (False, "memb")):
+            want_rec = arrays[f"{name}.{tag}.rec"].astype(np.int64)
+            want = arrays[f"{name}.{tag}.rows"].astype(np.int64)
+            for kw in ({}, {"rows_per_strip": 4, "emit_buf_records": 2}):
+                res, got = gpu_index(vals, recs, order, **kw)
+                assert_index_equal(got, (want_rec, want[:, 0], want[:, 1], want[:, 2]),
+                                   f"{name}/{tag}/{kw}")
+                n_general += res.general
+            for q in case["queries"]:
+                if q["membership"] != (not order):
+                    continue
+                m = want_rec == hdrs.index(q["rec"])
+                out, _ = gpu_query(want[m, 0], want[m, 1], want[m, 2], q["s"], q["e"], q["k"],
+                                   q["n"], q["membership"])
+                assert np.array_equal(out, arrays[q["key"]]), q
+    assert n_general > 0          # the arbitrary-integer cases must take the general path
+
+
+# ------------------------------------------------------------------ synthetic
+@pytest.mark.parametrize("C,dense", [(1, False), (9, False), (9, True), (93, False), (130, True)])
+def test_synth_matches_oracle(C, dense):
+    api = _api()
+    L = 70000
+    want = mo.synth_dap(L, C, seed=20240611 + C, dense=dense)
+    got = api.synth_dap(L, C, seed=20240611 + C, dense=dense).cpu().numpy()
+    assert np.array_equal(got, want)
+    part = api.synth_dap(L, C, seed=20240611 + C, row0=33333, rows=12345, dense=dense).cpu().numpy()
+    assert np.array_equal(part, want[33333:33333 + 12345])
+
+
+GEOMS = [1, 2, 4, 5, 8, 9, 12, 13, 16, 24, 25, 32, 33, 48, 64, 65, 93, 96, 128, 129, 192, 256, 300]
+
+
+@pytest.mark.parametrize("C", GEOMS)
+@pytest.mark.parametrize("order", [True, False])
+def test_index_valid_ms_all_geometries(C, order):
+    L = 20000 if C <= 128 else 6000
+    vals = mo.synth_dap(L, C, seed=C * 7 + 1, dense=(C % 2 == 0))
+    recs = [("chrS", L)]
+    want = mo.index_build(vals, recs, order)
+    res, got = gpu_index(vals, recs, order)
+    assert_index_equal(got, want, f"C={C} order={order}")
+    assert not res.irregular and not res.general
+    # tiny strips / tiny staging buffers: exercises look-back and the replay path
+    res, got = gpu_index(vals[:3000], [("chrS", 3000)], order, rows_per_strip=8, emit_buf_records=4)
+    assert_index_equal(got, mo.index_build(vals[:3000], [("chrS", 3000)], order), f"C={C} tiny")
+
+
+@pytest.mark.parametrize("C", [3, 9, 20, 40, 93, 150])
+@pytest.mark.parametrize("order", [True, False])
+def test_index_arbitrary_ints_general_path(C, order):
+    rng = np.random.default_rng(C)
+    lens = [700, 1, 2500, 1333]
+    L = sum(lens)
+    vals = rng.integers(0, 50, (L, C))
+    vals[rng.random((L, C)) < 0.3] = 0
+    recs = [(f"r{i}", n) for i, n in enumerate(lens)]
+    want = mo.index_build(vals, recs, order)
+    res, got = gpu_index(vals, recs, order, rows_per_strip=64)
+    assert res.irregular and res.general
+    assert_index_equal(got, want, f"C={C} order={order}")
+
+
+@pytest.mark.parametrize("order", [True, False])
+def test_index_multi_record_and_partial(order):
+    rng = np.random.default_rng(5)
+    C = 9
+    lens = [5000, 1, 1, 12000, 300, 7777]
+    recs = [(f"c{i}", n) for i, n in enumerate(lens)] + [("unused", 1000)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=100 + i, dense=(i % 2 == 0))
+                           for i, n in enumerate(lens)])
+    vals = vals[:-100]                      # DAP ends inside the last record it touches
+    want = mo.index_build(vals, recs, order)
+    res, got = gpu_index(vals, recs, order)
+    assert_index_equal(got, want, "multi")
+    assert not res.general
+
+
+def test_index_position_beyond_records_raises():
+    api = _api()
+    dap = torch.zeros((10, 2), dtype=torch.int32, device="cuda")
+    with pytest.raises(Exception, match="beyond all intervals"):
+        api.index_build(dap, [("a", 4)], True)
+
+
+def test_index_large_values_uint32_end():
+    # MEM end = p + length may exceed int32; ends are carried as uint32
+    C, L = 5, 300
+    vals = np.full((L, C), 2**31 - 1 - 100, dtype=np.int64)
+    vals[::7, 2] = 2**31 - 1
+    want = mo.index_build(vals, [("big", L)], True)
+    res, got = gpu_index(vals, [("big", L)], True)
+    assert_index_equal(got, want, "u32")
+
+
+# ------------------------------------------------------------------ queries
+@pytest.mark.parametrize("C,membership", [(9, False), (9, True), (93, False), (93, True), (40, True)])
+def test_query_vs_oracle(C, membership):
+    api = _api()
+    rng = np.random.default_rng(C + membership)
+    L = 60000
+    vals = mo.synth_dap(L, C, seed=C + 11, dense=True)
+    recs = [("chrQ", L)]
+    _, s, e, c = mo.index_build(vals, recs, not membership)
+    n_docs = C + 1
+    windows = [(0, L), (0, 1), (17, 8192 + 17), (L - 5, L + 40), (12345, 12345), (30000, 47001)]
+    for qs, qe in windows:
+        for k in (1, 2, 31, 101, 300):
+            want = mo.query(s, e, c, qs, qe, k, n_docs, membership)
+            got, dev = gpu_query(s, e, c, qs, qe, k, n_docs, membership)
+            assert np.array_equal(got, want), (qs, qe, k)
+    # text formatters, byte-identical to the reference's writers
+    want = mo.query(s, e, c, 100, 9000, 31, n_docs, membership)
+    got, dev = gpu_query(s, e, c, 100, 9000, 31, n_docs, membership)
+    if membership:
+        assert api.format_membership(dev, n_docs).decode() == mo.format_membership(want)
+    else:
+        assert api.format_conservation(dev).decode() == mo.format_conservation(want)
+
+
+def test_query_invariant_valid_ms():
+    # conservation == 1 + #{MS >= k} for valid matching statistics
+    L, C, k = 300000, 9, 31
+    api = _api()
+    dap = api.synth_dap(L, C, seed=20240612)
+    res = api.index_build(dap, [("chrS", L)], True)
+    out = api.query_conservation(res.start[:res.n], res.end[:res.n], res.order[:res.n], 0, L, k, C + 1)
+    want = 1 + (dap >= k).sum(dim=1)
+    assert torch.equal(out.to(torch.int64), want)
+
+
+def test_query_order_out_of_range_raises():
+    s = np.array([5, 9]); e = np.array([9, 12]); c = np.array([1, 7])
+    with pytest.raises(IndexError):
+        gpu_query(s, e, c, 0, 20, 3, 5, False)
+    with pytest.raises(IndexError):
+        gpu_query(s, e, c, 0, 20, 3, 5, True)
+
+
+def test_query_u16_many_docs():
+    s = np.array([5, 9, 14]); e = np.array([5, 9, 15]); c = np.array([300, 2, 999])
+    want = mo.query(s, e, c, 0, 30, 4, 1000, False)
+    got, _ = gpu_query(s, e, c, 0, 30, 4, 1000, False)
+    assert np.array_equal(got.astype(np.int64) & 0xFFFF, want)

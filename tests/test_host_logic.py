@@ -1,0 +1,179 @@
+"""Host-side logic and the C-ABI surface (no GPU needed)."""
+import io as _io
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pyarrow.parquet as pq
+import pytest
+
+from oracle import memo_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from memo_b200 import _build, _lib
+    _build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "memo_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(memo_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in memo_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.memo_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    from memo_b200 import _lib
+    assert C.sizeof(_lib.Segment) == 32 and _lib.Segment.pos0.offset == 16
+    assert C.sizeof(_lib.IndexOpts) == 32
+
+
+def test_segments_match_oracle_runs():
+    from memo_b200 import api
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        lens = [int(x) for x in rng.integers(0, 9, int(rng.integers(1, 6)))]
+        total = sum(lens)
+        if total == 0:
+            continue
+        a = int(rng.integers(0, total))
+        n = int(rng.integers(1, total - a + 1))
+        recs = [(f"r{i}", l) for i, l in enumerate(lens)]
+        segs = api.segments_for_rows(recs, a, n)
+        runs, rel = mo.split_runs(np.arange(a, a + n), recs)
+        assert [(s.rec_id, s.row_begin, s.row_begin + s.n_rows) for s in segs] == runs
+        for s in segs:
+            assert s.pos0 == rel[s.row_begin] and s.rec_len == lens[s.rec_id]
+
+
+def test_segments_beyond_records_raise():
+    from memo_b200 import api
+    with pytest.raises(Exception, match="beyond all intervals"):
+        api.segments_for_rows([("a", 5)], 0, 6)
+
+
+def test_dap_text_ingest_and_bed_writer(example_golden, tmp_path):
+    from memo_b200 import io
+    p = tmp_path / "dap.txt"
+    p.write_text(example_golden["dap_txt"])
+    pos0, dap = io.read_dap_text(str(p))
+    assert pos0 == 0 and np.array_equal(dap, example_golden["vals"])
+    rows = mo.index_build(dap, example_golden["records"], True)
+    buf = _io.BytesIO()
+    io.write_bed(io.index_table(example_golden["records"], *rows), buf)
+    assert buf.getvalue().decode() == example_golden["cons_bed"]
+    bad = tmp_path / "bad.txt"
+    bad.write_text("0 1 2\n2 1 2\n")
+    with pytest.raises(Exception, match="consecutive"):
+        io.read_dap_text(str(bad))
+
+
+def test_parquet_compress_bed_cli(example_golden, tmp_path):
+    bed = tmp_path / "x.bed"
+    bed.write_text(example_golden["cons_bed"])
+    out = tmp_path / "x.parquet"
+    r = subprocess.run([sys.executable, "-m", "memo_b200.parquet_compress_bed", "-f", str(bed), "-o", str(out)],
+                       cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "DONE index compression" in r.stdout
+    t = pq.read_table(str(out))
+    assert [f.name for f in t.schema] == ["f0", "f1", "f2", "f3"]
+    assert [str(f.type) for f in t.schema] == ["string", "int64", "int64", "int64"]
+    assert t.schema.metadata is None
+    assert pq.ParquetFile(str(out)).metadata.row_group(0).column(1).compression == "ZSTD"
+    want = [l.split("\t") for l in example_golden["cons_bed"].splitlines()]
+    assert t.column("f0").to_pylist() == [w[0] for w in want]
+    for j in (1, 2, 3):
+        assert t.column(f"f{j}").to_pylist() == [int(w[j]) for w in want]
+    # the reader keeps the live predicate of memo_query.py:25-27
+    from memo_b200 import io
+    f1, f2, f3 = io.read_index_rows(str(out), "ref_1", 4, 9)
+    assert f1.tolist() == [int(w[1]) for w in want if 4 < int(w[1]) < 9]
+
+
+def test_dap_to_bed_argument_checks(tmp_path):
+    from memo_b200 import dap_to_bed as d
+    fai = tmp_path / "p.fai"; fai.write_text("a\t3\n")
+    dap = tmp_path / "dap.txt"; dap.write_text("0 1\n")
+    ok = d.parse_arguments(["--mem", "--overlap", "--order", "--fai", str(fai), "--dap", str(dap)])
+    d.check_args(ok)
+    assert ok.sort_lcps and ok.print_overlaps
+    with pytest.raises(Exception, match="fai file does not exist"):
+        d.check_args(d.parse_arguments(["--mem", "--fai", "nope.fai", "--dap", str(dap)]))
+    with pytest.raises(Exception, match="incorrect file extension"):
+        d.check_args(d.parse_arguments(["--mem", "--fai", str(dap), "--dap", str(dap)]))
+    with pytest.raises(Exception, match="Either print MSs or MEMs"):
+        d.check_args(d.parse_arguments(["--fai", str(fai), "--dap", str(dap)]))
+    with pytest.raises(Exception, match="Either print MSs or MEMs"):
+        d.check_args(d.parse_arguments(["--ms", "--mem", "--fai", str(fai), "--dap", str(dap)]))
+    with pytest.raises(Exception, match="Can only print overlaps"):
+        d.check_args(d.parse_arguments(["--ms", "--overlap", "--fai", str(fai), "--dap", str(dap)]))
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from memo_b200 import api, _lib
+    with pytest.raises(_lib.MemoError):
+        api.IndexBuilder()
+    with pytest.raises(_lib.MemoError):
+        api.synth_dap(100, 3, 1)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "memo_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".sh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "oracle/" not in src.replace("oracle/memo_oracle.py:synth_dap", ""), f
+
+
+def test_shard_plans_cover_everything():
+    from memo_b200 import shard
+    rng = np.random.default_rng(11)
+    for _ in range(100):
+        lens = [int(x) for x in rng.integers(1, 50, int(rng.integers(1, 5)))]
+        recs = [(f"r{i}", l) for i, l in enumerate(lens)]
+        total = sum(lens)
+        world = int(rng.integers(1, 9))
+        covered = 0
+        for rank in range(world):
+            p = shard.plan_shard(recs, total, world, rank, halo_right=7)
+            assert p.pos_lo == covered
+            covered = p.pos_hi
+            owned = p.segs[:p.n_owned]
+            assert sum(s.n_rows for s in owned) == p.pos_hi - p.pos_lo
+            for s in p.segs:
+                assert s.row_begin >= (0 if s.flags & 1 else 1)
+                assert s.row_begin + s.n_rows <= p.buf_hi - p.buf_lo
+        assert covered == total
+
+
+def test_sharded_build_equals_whole_on_oracle():
+    """Shard plans fed to the C oracle (same run semantics as the device ABI):
+    concatenating the owned rows of every rank reproduces the unsharded index."""
+    from memo_b200 import shard
+    from oracle import c_oracle as co
+    lens = [3000, 1, 4500, 2500]
+    recs = [(f"c{i}", l) for i, l in enumerate(lens)]
+    C = 6
+    vals = np.concatenate([mo.synth_dap(n, C, seed=50 + i, dense=True) for i, n in enumerate(lens)])
+    whole = co.index_build(vals, recs, True)
+    for world in (1, 2, 3, 4, 8):
+        parts = []
+        for rank in range(world):
+            p = shard.plan_shard(recs, len(vals), world, rank, halo_right=40)
+            segs = [co.Seg(s.row_begin, s.n_rows, s.pos0, s.rec_len, s.rec_id, s.flags)
+                    for s in p.segs[:p.n_owned]]
+            parts.append(co.index_build(vals[p.buf_lo:p.buf_hi], recs, True, segs=segs))
+        for j in range(4):
+            assert np.array_equal(np.concatenate([q[j] for q in parts]), whole[j]), world
