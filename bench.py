@@ -180,11 +180,11 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--rows-per-strip", type=int, default=0)
+    ap.add_argument("--rows-per-tile", type=int, default=0)
     ap.add_argument("--emit-buf", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--pipeline", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -221,8 +221,8 @@ def main():
     if buf_hi > hi:
         segs.append(api.Segment(row_begin=hi - buf_lo, n_rows=buf_hi - hi, pos0=hi, rec_len=rec_len,
                                 rec_id=0, flags=0))
-    tuning = dict(rows_per_strip=args.rows_per_strip, emit_buf_records=args.emit_buf,
-                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, pipeline=args.pipeline)
+    tuning = dict(rows_per_tile=args.rows_per_tile, emit_buf_records=args.emit_buf,
+                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages)
     builder = api.IndexBuilder(dev)
     seg_out_end = torch.zeros(len(segs), dtype=torch.int64, device=dev)
     # size the outputs with a counting run

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 1
+#define MEMO_B200_ABI_VERSION 2
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -58,11 +58,11 @@ typedef struct memo_segment {
 
 typedef struct memo_index_opts {
     int32_t order_mode;       /* 1 = --order (conservation), 0 = membership */
-    int32_t rows_per_strip;   /* 0 = default */
-    int32_t emit_buf_records; /* staged records per strip, 0 = default */
-    int32_t warps_per_cta;    /* 0 = default */
-    int32_t ctas_per_sm;      /* 0 = default */
-    int32_t pipeline;         /* 0 = default, 1 = ld.global rows, 2 = bulk-async staged */
+    int32_t rows_per_tile;    /* DAP rows per shared-memory tile (general build: per strip), 0 = default */
+    int32_t emit_buf_records; /* index rows staged in shared memory per lane group, 0 = default */
+    int32_t warps_per_cta;    /* 0 = default (8) */
+    int32_t ctas_per_sm;      /* cap on resident CTAs per SM, 0 = as many as fit */
+    int32_t stages;           /* bulk-copy pipeline depth per CTA, 0 = default (2), max 4 */
     int32_t reserved[2];
 } memo_index_opts_t;
 
@@ -71,7 +71,7 @@ typedef struct memo_index_opts {
 #define MEMO_RES_IRREGULAR 1 /* != 0: input is not valid matching statistics;
                                 the fast build's output must be discarded and
                                 memo_index_build_general run instead */
-#define MEMO_RES_REPLAYS 2   /* strips whose staging buffer overflowed (stat) */
+#define MEMO_RES_REPLAYS 2   /* tiles whose staging buffer overflowed (stat) */
 #define MEMO_RES_SLOTS 4
 
 int memo_abi_version(void);
@@ -80,8 +80,10 @@ const char* memo_last_error(void);
 /* Number of SMs of the current device (grid sizing is in multiples of it). */
 int memo_device_sm_count(void);
 
-/* Bytes of device scratch memo_index_build{,_general} need. */
-size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols,
+/* Bytes of device scratch memo_index_build{,_general} need for outputs of
+ * out_cap entries (the single-pass build stages its index rows there before
+ * the ordered copy into out_*). */
+size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int64_t out_cap,
                                   const memo_segment_t* segs, int32_t n_seg,
                                   const memo_index_opts_t* opts);
 
@@ -100,10 +102,12 @@ size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols,
  *               run i (so run i owns rows [seg_out_end[i-1], seg_out_end[i]))
  *  result       device int64 [MEMO_RES_SLOTS]
  *
- * Single pass over the DAP.  Exact for every input for which
- * result[MEMO_RES_IRREGULAR] comes back 0 (always the case for matching
- * statistics, MS[p] >= MS[p-1]-1); otherwise call memo_index_build_general.
- * Rows past out_cap are counted but not stored. */
+ * Single pass over the DAP (bulk async copies into shared-memory tiles).  Exact
+ * for every input for which result[MEMO_RES_IRREGULAR] comes back 0 -- no
+ * p + length ever decreases down a column, always the case for matching
+ * statistics (MS[p] >= MS[p-1]-1); otherwise the output must be discarded and
+ * memo_index_build_general called.  Rows past out_cap are counted but not
+ * stored.  n_cols <= 512. */
 int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld,
                      const memo_segment_t* segs, int32_t n_seg,
                      const memo_index_opts_t* opts,

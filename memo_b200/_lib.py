@@ -24,9 +24,9 @@ class Segment(C.Structure):
 
 class IndexOpts(C.Structure):
     """memo_index_opts_t"""
-    _fields_ = [("order_mode", C.c_int32), ("rows_per_strip", C.c_int32),
+    _fields_ = [("order_mode", C.c_int32), ("rows_per_tile", C.c_int32),
                 ("emit_buf_records", C.c_int32), ("warps_per_cta", C.c_int32),
-                ("ctas_per_sm", C.c_int32), ("pipeline", C.c_int32),
+                ("ctas_per_sm", C.c_int32), ("stages", C.c_int32),
                 ("reserved", C.c_int32 * 2)]
 
 
@@ -36,7 +36,8 @@ SIGNATURES = {
     "memo_abi_version": (C.c_int, []),
     "memo_last_error": (C.c_char_p, []),
     "memo_device_sm_count": (C.c_int, []),
-    "memo_index_workspace_bytes": (_sz, [_i64, _i32, C.POINTER(Segment), _i32, C.POINTER(IndexOpts)]),
+    "memo_index_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64, C.POINTER(Segment), _i32,
+                                         C.POINTER(IndexOpts)]),
     "memo_index_build": (C.c_int, [_vp, _i64, _i32, _i32, C.POINTER(Segment), _i32,
                                    C.POINTER(IndexOpts), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "memo_index_build_general": (C.c_int, [_vp, _i64, _i32, _i32, C.POINTER(Segment), _i32,

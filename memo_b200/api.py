@@ -122,11 +122,11 @@ class IndexRows:
         return rec, start, end, order
 
 
-def _opts(order: bool, rows_per_strip=0, emit_buf_records=0, warps_per_cta=0, ctas_per_sm=0,
-          pipeline=0) -> IndexOpts:
-    return IndexOpts(order_mode=1 if order else 0, rows_per_strip=rows_per_strip,
+def _opts(order: bool, rows_per_tile=0, emit_buf_records=0, warps_per_cta=0, ctas_per_sm=0,
+          stages=0) -> IndexOpts:
+    return IndexOpts(order_mode=1 if order else 0, rows_per_tile=rows_per_tile,
                      emit_buf_records=emit_buf_records, warps_per_cta=warps_per_cta,
-                     ctas_per_sm=ctas_per_sm, pipeline=pipeline)
+                     ctas_per_sm=ctas_per_sm, stages=stages)
 
 
 class IndexBuilder:
@@ -157,11 +157,12 @@ class IndexBuilder:
         rows, ld = dap.shape
         seg_arr = (Segment * max(len(segs), 1))(*segs)
         opts = _opts(order, **tuning)
-        need = self.lib.memo_index_workspace_bytes(rows, n_cols, seg_arr, len(segs), C.byref(opts))
+        cap = 0 if out is None else out[0].numel()
+        need = self.lib.memo_index_workspace_bytes(rows, n_cols, ld, cap, seg_arr, len(segs),
+                                                   C.byref(opts))
         if need == 0:
             raise MemoError("memo_index_workspace_bytes: " + self.lib.memo_last_error().decode())
         ws = self._workspace(need)
-        cap = 0 if out is None else out[0].numel()
         o0, o1, o2 = (None, None, None) if out is None else out
         stream = _stream_ptr(self.device)
         if general:

@@ -35,4 +35,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int device_sm_count();
 
+// scratch the general (three-pass) index build needs (index_general.cu)
+size_t general_workspace_bytes(int64_t rows, int32_t n_cols, const memo_segment_t* segs,
+                               int32_t n_seg, const memo_index_opts_t* opts);
+
 }  // namespace memo

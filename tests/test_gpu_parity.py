@@ -79,7 +79,7 @@ def test_fuzz_goldens(fuzz_golden):
         for order, tag in ((True, "cons"), (False, "memb")):
             want_rec = arrays[f"{name}.{tag}.rec"].astype(np.int64)
             want = arrays[f"{name}.{tag}.rows"].astype(np.int64)
-            for kw in ({}, {"rows_per_strip": 4, "emit_buf_records": 2}):
+            for kw in ({}, {"rows_per_tile": 4, "emit_buf_records": 2}):
                 res, got = gpu_index(vals, recs, order, **kw)
                 assert_index_equal(got, (want_rec, want[:, 0], want[:, 1], want[:, 2]),
                                    f"{name}/{tag}/{kw}")
@@ -120,7 +120,7 @@ def test_index_valid_ms_all_geometries(C, order):
     assert_index_equal(got, want, f"C={C} order={order}")
     assert not res.irregular and not res.general
     # tiny strips / tiny staging buffers: exercises look-back and the replay path
-    res, got = gpu_index(vals[:3000], [("chrS", 3000)], order, rows_per_strip=8, emit_buf_records=4)
+    res, got = gpu_index(vals[:3000], [("chrS", 3000)], order, rows_per_tile=8, emit_buf_records=4)
     assert_index_equal(got, mo.index_build(vals[:3000], [("chrS", 3000)], order), f"C={C} tiny")
 
 
@@ -134,7 +134,7 @@ def test_index_arbitrary_ints_general_path(C, order):
     vals[rng.random((L, C)) < 0.3] = 0
     recs = [(f"r{i}", n) for i, n in enumerate(lens)]
     want = mo.index_build(vals, recs, order)
-    res, got = gpu_index(vals, recs, order, rows_per_strip=64)
+    res, got = gpu_index(vals, recs, order, rows_per_tile=64)
     assert res.irregular and res.general
     assert_index_equal(got, want, f"C={C} order={order}")
 
