@@ -149,8 +149,10 @@ class IndexBuilder:
     def launch(self, dap: torch.Tensor, n_cols: int, segs: Sequence[Segment], order: bool,
                out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], seg_out_end: torch.Tensor,
                general: bool = False, carry_in: Optional[torch.Tensor] = None,
-               carry_out: Optional[torch.Tensor] = None, **tuning) -> None:
-        """Enqueue one build on the current stream (no synchronisation)."""
+               carry_out: Optional[torch.Tensor] = None, result: Optional[torch.Tensor] = None,
+               **tuning) -> None:
+        """Enqueue one build on the current stream (no synchronisation).  `result`
+        (device int64 [RES_SLOTS]) replaces the builder's own result slots."""
         _require_cuda(dap, "dap")
         if dap.dtype != torch.int32 or dap.dim() != 2:
             raise MemoError("dap must be int32 [rows, ld]")
@@ -165,17 +167,18 @@ class IndexBuilder:
         ws = self._workspace(need)
         o0, o1, o2 = (None, None, None) if out is None else out
         stream = _stream_ptr(self.device)
+        res_ptr = self._result.data_ptr() if result is None else result.data_ptr()
         if general:
             rc = self.lib.memo_index_build_general(
                 dap.data_ptr(), rows, n_cols, ld, seg_arr, len(segs), C.byref(opts),
                 _ptr(carry_in), _ptr(carry_out), _ptr(o0), _ptr(o1), _ptr(o2), cap,
-                _ptr(seg_out_end), self._result.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                _ptr(seg_out_end), res_ptr, ws.data_ptr(), ws.numel(), stream)
             _lib.check(rc, "memo_index_build_general")
         else:
             rc = self.lib.memo_index_build(
                 dap.data_ptr(), rows, n_cols, ld, seg_arr, len(segs), C.byref(opts),
                 _ptr(o0), _ptr(o1), _ptr(o2), cap, _ptr(seg_out_end),
-                self._result.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                res_ptr, ws.data_ptr(), ws.numel(), stream)
             _lib.check(rc, "memo_index_build")
 
     def result(self) -> Tuple[int, bool, int]:

@@ -49,7 +49,7 @@ namespace {
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_TILE_ROWS = 960;
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gather block
 
 struct TileDesc {

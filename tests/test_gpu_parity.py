@@ -220,3 +220,76 @@ def test_query_u16_many_docs():
     want = mo.query(s, e, c, 0, 30, 4, 1000, False)
     got, _ = gpu_query(s, e, c, 0, 30, 4, 1000, False)
     assert np.array_equal(got.astype(np.int64) & 0xFFFF, want)
+
+
+# ------------------------------------------------------------------ host-buffer API and CLIs
+@pytest.mark.parametrize("order", [True, False])
+def test_host_build_index_streams_in_chunks(order):
+    from memo_b200 import host
+    C = 9
+    lens = [30000, 1, 7, 52000, 300]
+    recs = [(f"c{i}", n) for i, n in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=7 + i, dense=(i == 3)) for i, n in enumerate(lens)])
+    want = mo.index_build(vals, recs, order)
+    for chunk_bytes in (64 << 20, 100_000, 36 * 1000):          # 1, ~30 and ~82 chunks; dense run overflows
+        stats = {}
+        got = host.build_index(vals.astype(np.int32), recs, order, chunk_bytes=chunk_bytes, stats=stats)
+        assert_index_equal(got, want, f"chunk_bytes={chunk_bytes}")
+        assert not stats["general"]
+    raw = host.build_index(vals.astype(np.int32), recs, order, chunk_bytes=100_000, raw=True)
+    assert raw.start.dtype == np.int32 and raw.end.dtype == np.uint32 and raw.n == want[1].size
+    assert_index_equal(raw.as_int64(), want, "raw")
+
+
+def test_host_build_index_irregular_falls_back():
+    from memo_b200 import host
+    rng = np.random.default_rng(3)
+    vals = rng.integers(0, 40, (5000, 6))
+    recs = [("a", 3000), ("b", 2000)]
+    stats = {}
+    got = host.build_index(vals.astype(np.int32), recs, True, chunk_bytes=20_000, stats=stats)
+    assert stats["general"]
+    assert_index_equal(got, mo.index_build(vals, recs, True), "irregular")
+
+
+def test_host_query_matches_oracle():
+    from memo_b200 import host
+    C, L = 9, 40000
+    vals = mo.synth_dap(L, C, seed=5, dense=True)
+    _, s, e, c = mo.index_build(vals, [("q", L)], True)
+    want = mo.query(s, e, c, 10, L - 3, 31, C + 1, False)
+    assert np.array_equal(host.query(s, e, c, 10, L - 3, 31, C + 1, False), want)
+    raw = host.query(s.astype(np.int32), e.astype(np.uint32), c.astype(np.int32), 10, L - 3, 31, C + 1,
+                     False, raw=True, trusted=True)
+    assert raw.dtype == np.uint8 and np.array_equal(raw.astype(np.int64), want)
+    # unsorted rows are accepted (painting is order independent)
+    perm = np.random.default_rng(0).permutation(s.size)
+    assert np.array_equal(host.query(s[perm], e[perm], c[perm], 10, L - 3, 31, C + 1, False), want)
+
+
+def test_cli_round_trip_example(example_golden, tmp_path, capsysbinary):
+    """dap.txt -> BED (dap_to_bed) -> Parquet (parquet_compress_bed) -> query text
+    (memo_query), byte-identical to the reference-generated goldens."""
+    from memo_b200 import dap_to_bed, memo_query, parquet_compress_bed
+    g = example_golden
+    dap = tmp_path / "dap.txt"; dap.write_text(g["dap_txt"])
+    fai = tmp_path / "ref_1.fa.fai"
+    fai.write_text("".join(f"{h}\t{n}\t7\t{n}\t{n + 1}\n" for h, n in g["records"]))
+    for order, bed_key, tag in ((True, "cons_bed", "cons"), (False, "memb_bed", "memb")):
+        argv = ["--mem", "--overlap", "--fai", str(fai), "--dap", str(dap)] + (["--order"] if order else [])
+        args = dap_to_bed.parse_arguments(argv)
+        dap_to_bed.check_args(args)
+        bed = tmp_path / f"{tag}.bed"
+        with open(bed, "wb") as fh:
+            dap_to_bed.main(args, sink=fh)
+        assert bed.read_text() == g[bed_key]
+        pq_path = tmp_path / f"{tag}.parquet"
+        parquet_compress_bed.main(parquet_compress_bed.parse_arguments(["-f", str(bed), "-o", str(pq_path)]))
+        capsysbinary.readouterr()
+        for q in g["queries"]:
+            if q["membership"] != (not order):
+                continue
+            out = tmp_path / "q.txt"
+            argv = ["-b", str(pq_path), "-r", q["region"], "-k", str(q["k"]), "-n", str(q["n"]), "-o", str(out)]
+            memo_query.main(memo_query.parse_arguments(argv + (["-m"] if q["membership"] else [])))
+            assert out.read_text() == q["out"], q
