@@ -5,6 +5,15 @@ from its own DAP rows plus a one-row left halo (the flag compares a row with its
 predecessor) and, for queries, a right halo of k_max-1 rows.  The only exchange
 is an all-gather of one int64 per rank -- the number of index rows a rank owns --
 whose exclusive prefix is the rank's offset in the ordered index.
+
+Input that is not valid matching statistics (the reference never validates,
+SURVEY A.1) needs one more exchange: the per-column end of the last flagged MEM
+has to cross shard boundaries, so the ranks agree on the irregular verdict
+(all-reduce of one flag), all-gather their per-column carries (n_cols x uint32
+per rank) and re-run the exact three-pass build with the carry handed in.
+
+Every collective here works on the tensors' own device: NCCL for CUDA tensors on
+the GPU box, gloo for the CPU tensors of the world_size-2 tests.
 """
 from __future__ import annotations
 
@@ -14,7 +23,9 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from ._lib import MEMO_SEG_CHR_END, MEMO_SEG_PRIMED, Segment
+from ._lib import MEMO_SEG_CHR_END, MEMO_SEG_PRIMED, MemoError, Segment
+
+NONE32 = 0xFFFFFFFF          # "no flagged row" in a carry vector (uint32 bits)
 
 
 @dataclass
@@ -85,3 +96,120 @@ def ordered_offsets(n_local: torch.Tensor, group=None) -> Tuple[torch.Tensor, to
     dist.all_gather_into_tensor(counts, n_local.reshape(1), group=group)
     rank = dist.get_rank(group)
     return counts, counts[:rank].sum()
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def agree_irregular(irregular: bool, device, group=None) -> bool:
+    """True on every rank iff any rank's shard is not valid matching statistics."""
+    if _world(group) == 1:
+        return bool(irregular)
+    t = torch.tensor([1 if irregular else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
+def carry_in_from_gathered(carries: torch.Tensor, rank: int) -> torch.Tensor:
+    """carries: int64 [world, C] of per-shard carry-outs (NONE32 = the shard flagged
+    nothing in that column and handed nothing on).  The carry into `rank` is the
+    closest earlier shard's value per column.  A shard hands on NONE32 only when
+    it is a single run that continues its record, so the walk back never leaves
+    the record of `rank`'s first run (a record's first row is always flagged)."""
+    C = carries.shape[1]
+    out = torch.full((C,), NONE32, dtype=torch.int64, device=carries.device)
+    for q in range(rank):
+        row = carries[q]
+        out = torch.where(row != NONE32, row, out)
+    return out
+
+
+def exchange_carries(carry_out: torch.Tensor, group=None) -> torch.Tensor:
+    """carry_out: int64 [C] (uint32 values) of this rank.  All-gather over the
+    ranks; returns the carry into this rank (int64 [C], NONE32 where none)."""
+    if _world(group) == 1:
+        return torch.full_like(carry_out, NONE32)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    allc = torch.empty((world, carry_out.numel()), dtype=carry_out.dtype, device=carry_out.device)
+    dist.all_gather_into_tensor(allc, carry_out.reshape(1, -1).contiguous(), group=group)
+    return carry_in_from_gathered(allc, rank)
+
+
+def gather_index_rows(cols: torch.Tensor, counts: torch.Tensor, dst: int = 0, group=None):
+    """The final ordered write: rank `dst` receives every rank's owned index rows
+    (cols: int32 [3, n_local]; counts: the all-gathered row counts) and returns
+    them concatenated in rank order = the reference's print order; the other ranks
+    return None.  Point-to-point so that no rank pads to the largest shard."""
+    if _world(group) == 1:
+        return cols
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = [int(c) for c in counts.tolist()]
+    if rank != dst:
+        if n[rank]:
+            dist.send(cols.contiguous(), dst=dst, group=group)
+        return None
+    out = torch.empty((3, sum(n)), dtype=cols.dtype, device=cols.device)
+    off = 0
+    for r in range(world):
+        if n[r]:
+            if r == rank:
+                out[:, off:off + n[r]] = cols
+            else:
+                buf = torch.empty((3, n[r]), dtype=cols.dtype, device=cols.device)
+                dist.recv(buf, src=r, group=group)
+                out[:, off:off + n[r]] = buf
+        off += n[r]
+    return out
+
+
+def build_index_sharded(dap: torch.Tensor, plan: ShardPlan, n_cols: int, order: bool,
+                        builder=None, group=None, **tuning):
+    """Index rows of this rank's position shard (`dap` = device rows
+    [plan.buf_lo, plan.buf_hi) of the pivot), exact for every input.
+
+    Returns (IndexRows, counts[world], offset): the rows this rank owns, every
+    rank's row count and this rank's exclusive offset in the ordered index.
+    """
+    from . import api
+    if not dap.is_cuda:
+        raise MemoError("build_index_sharded needs the shard on a CUDA device (no CPU fallback)")
+    dev = dap.device
+    builder = api.IndexBuilder(dev) if builder is None else builder
+    owned = plan.segs[:plan.n_owned]
+    n_rows = plan.pos_hi - plan.pos_lo
+    seg_out_end = torch.zeros(max(len(owned), 1), dtype=torch.int64, device=dev)
+    cap = max(1024, int(n_rows * n_cols * 0.02) + n_cols * (len(owned) + 1))
+    general = False
+    while True:
+        out = tuple(torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3))
+        builder.launch(dap, n_cols, owned, order, out, seg_out_end, **tuning)
+        n, irregular, replays = builder.result()
+        if n <= cap:
+            break
+        cap = n
+    if agree_irregular(irregular, dev, group):
+        general = True
+        carry_out = torch.full((n_cols,), -1, dtype=torch.int32, device=dev)      # NONE32 bits
+        builder.launch(dap, n_cols, owned, order, None, seg_out_end, general=True,
+                       carry_out=carry_out, **tuning)
+        n, _, _ = builder.result()
+        carry64 = carry_out.to(torch.int64) & NONE32
+        carry_in = exchange_carries(carry64, group)
+        carry_in32 = carry_in.to(torch.int32)           # wraps back to the uint32 bit pattern
+        out = tuple(torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(3))
+        while True:
+            builder.launch(dap, n_cols, owned, order, out, seg_out_end, general=True,
+                           carry_in=carry_in32, **tuning)
+            n2, _, replays = builder.result()
+            if n2 <= out[0].numel():
+                n = n2
+                break
+            out = tuple(torch.empty(n2, dtype=torch.int32, device=dev) for _ in range(3))
+    rows = api.IndexRows(start=out[0], end=out[1], order=out[2],
+                         seg_out_end=seg_out_end[:len(owned)].cpu(),
+                         seg_rec_id=[s.rec_id for s in owned], n=n, irregular=general,
+                         replays=replays, general=general)
+    n_local = torch.tensor([n], dtype=torch.int64, device=dev)
+    counts, offset = ordered_offsets(n_local, group)
+    return rows, counts, offset
