@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="index kernel variant (1 = generic warp-stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -222,7 +223,8 @@ def main():
         segs.append(api.Segment(row_begin=hi - buf_lo, n_rows=buf_hi - hi, pos0=hi, rec_len=rec_len,
                                 rec_id=0, flags=0))
     tuning = dict(rows_per_tile=args.rows_per_tile, emit_buf_records=args.emit_buf,
-                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages)
+                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages,
+                  kernel_variant=args.variant)
     builder = api.IndexBuilder(dev)
     seg_out_end = torch.zeros(len(segs), dtype=torch.int64, device=dev)
     # size the outputs with a counting run

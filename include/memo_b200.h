@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 2
+#define MEMO_B200_ABI_VERSION 3
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -63,7 +63,8 @@ typedef struct memo_index_opts {
     int32_t warps_per_cta;    /* 0 = default (8) */
     int32_t ctas_per_sm;      /* cap on resident CTAs per SM, 0 = as many as fit */
     int32_t stages;           /* bulk-copy pipeline depth per CTA, 0 = default (2), max 4 */
-    int32_t reserved[2];
+    int32_t kernel_variant;   /* 0 = pick, 1 = force the generic warp-stream kernel (tests) */
+    int32_t reserved;
 } memo_index_opts_t;
 
 /* slots of the device `result` array written by memo_index_build* */

@@ -27,7 +27,7 @@ class IndexOpts(C.Structure):
     _fields_ = [("order_mode", C.c_int32), ("rows_per_tile", C.c_int32),
                 ("emit_buf_records", C.c_int32), ("warps_per_cta", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("stages", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("kernel_variant", C.c_int32), ("reserved", C.c_int32)]
 
 
 # symbol -> (restype, argtypes); must list every function include/memo_b200.h declares

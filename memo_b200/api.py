@@ -123,10 +123,10 @@ class IndexRows:
 
 
 def _opts(order: bool, rows_per_tile=0, emit_buf_records=0, warps_per_cta=0, ctas_per_sm=0,
-          stages=0) -> IndexOpts:
+          stages=0, kernel_variant=0) -> IndexOpts:
     return IndexOpts(order_mode=1 if order else 0, rows_per_tile=rows_per_tile,
                      emit_buf_records=emit_buf_records, warps_per_cta=warps_per_cta,
-                     ctas_per_sm=ctas_per_sm, stages=stages)
+                     ctas_per_sm=ctas_per_sm, stages=stages, kernel_variant=kernel_variant)
 
 
 class IndexBuilder:

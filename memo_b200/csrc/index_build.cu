@@ -41,90 +41,10 @@
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in
 // result[MEMO_RES_IRREGULAR].
-#include "common.cuh"
+#include "index_fast.cuh"
 
 namespace memo {
 namespace {
-
-constexpr int MAX_STAGES = 4;
-constexpr int MAX_TILE_ROWS = 960;
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gather block
-
-struct TileDesc {
-    int n;              // compare rows 1..n (row 0 of the tile is the predecessor row)
-    int off;            // word offset of row 0 inside the stage data
-    uint32_t pos_h;     // record-relative position of row 0
-    uint32_t rec_len;
-    int flags;          // 1 = last tile of its run, 2 = chr-end rows follow the run
-    int pad[3];
-};
-
-struct FastParams {
-    const int32_t* dap;
-    long long total_bytes;             // rows * ld * 4
-    int32_t C;
-    int32_t ld;
-    const memo_segment_t* segs;        // device copy
-    const long long* seg_tile_start;   // device [n_seg + 1]
-    int32_t n_seg;
-    long long n_tiles;
-    int32_t T;                         // compare rows per tile
-    int32_t K;                         // staged index rows per group
-    int32_t stages;
-    uint32_t stage_bytes;
-    uint32_t warp_smem;                // shared-memory bytes per warp
-    uint32_t off_bars, off_descs, off_stg, off_list;   // inside the warp's region
-    int32_t gw;                        // phase B: lanes per row group (KPL == 1)
-    int32_t all_pairs;                 // phase B: all-pairs counting (narrow rows)
-    int32_t sl, wcols, rb;             // phase A: lanes per row, columns per lane, rows per lane
-    uint32_t* scr_start;               // scratch index rows (unordered tile blocks)
-    uint32_t* scr_end;
-    uint32_t* scr_order;
-    long long out_cap;
-    uint32_t* tile_cnt;                // [n_tiles]
-    unsigned long long* tile_off;      // [n_tiles] scratch offset of the tile's block
-    unsigned long long* cursor;        // scratch allocation cursor
-    int64_t* result;
-};
-
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// 1-D bulk async copy global -> shared (TMA engine), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_addr(dst)),
-        "l"(src), "r"(bytes), "r"(smem_addr(bar))
-        : "memory");
-}
 
 // ---------------------------------------------------------------- kernel 1
 // KPL = DAP columns per lane in phase B (1: a row is handled by a group of
@@ -200,7 +120,7 @@ __global__ void __launch_bounds__(256) stream_kernel(const FastParams P) {
         d.pos_h = (uint32_t)(seg.pos0 - (1 - primed)) + (uint32_t)(t * P.T);
         d.rec_len = (uint32_t)seg.rec_len;
         d.flags = ((tile + 1 == c_hi) ? 1 : 0) | ((seg.flags & MEMO_SEG_CHR_END) ? 2 : 0);
-        d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        d.r_lo = 1; d.r_hi = (int)n; d.pad = 0;
         descs[s] = d;
         unsigned char* data = wbase + (size_t)s * P.stage_bytes + 16;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.dap);
@@ -668,16 +588,7 @@ void set_scan_shape(int C, int T, Geometry* geo) {
     geo->rb = 0;
 }
 
-typedef void (*stream_kernel_t)(const FastParams);
-
 stream_kernel_t select_kernel(const Geometry& g, bool order, int C, int ld) {
-    // shapes with fully unrolled column loops (the reference configurations)
-    if (g.KPL == 1 && g.sl == 1 && ld == C) {
-#define MEMO_CT(CC) \
-    if (C == CC) return order ? stream_kernel<1, true, CC> : stream_kernel<1, false, CC>;
-        MEMO_CT(4) MEMO_CT(9)
-#undef MEMO_CT
-    }
 #define MEMO_CASE(KK) \
     if (g.KPL == KK) return order ? stream_kernel<KK, true, 0> : stream_kernel<KK, false, 0>;
     MEMO_CASE(1) MEMO_CASE(2) MEMO_CASE(3) MEMO_CASE(4) MEMO_CASE(6) MEMO_CASE(8) MEMO_CASE(16)
@@ -687,6 +598,7 @@ stream_kernel_t select_kernel(const Geometry& g, bool order, int C, int ld) {
 
 struct FastPlan {
     Geometry geo;
+    int narrow, rpl;            // lane-per-row kernel (index_narrow.cu) and its rows per lane
     int T, K, stages, warps, ctas_per_sm;
     uint32_t stage_bytes, warp_smem, off_bars, off_descs, off_stg, off_list;
     long long n_tiles, n_blocks;
@@ -711,27 +623,46 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     MEMO_REQUIRE(plan->stages <= MAX_STAGES, "stages must be <= %d", MAX_STAGES);
     plan->ctas_per_sm = (opts && opts->ctas_per_sm > 0) ? opts->ctas_per_sm : 0;
     const long long row_bytes = (long long)ld * 4;
-    // a stage holds T + 2 rows; keep a warp's stages within its share of the SM
-    const long long stage_budget = (200 * 1024 / plan->warps - 1536) / plan->stages;
+    plan->rpl = 1;
+    plan->narrow = (ld == C && !(opts && opts->kernel_variant == 1) &&
+                    select_narrow_kernel(C, true, &plan->rpl) != nullptr) ? 1 : 0;
+    if (!plan->narrow) plan->rpl = 1;
     long long T;
-    if (opts && opts->rows_per_tile > 0) {
-        T = opts->rows_per_tile;
+    if (plan->narrow) {
+        // whole warp steps of 32 * rpl rows, ~4.5-9 KB of DAP per tile
+        const long long step = 32ll * plan->rpl;
+        long long it = (opts && opts->rows_per_tile > 0) ? (opts->rows_per_tile + step - 1) / step
+                                                          : (5632 + step * row_bytes - 1) / (step * row_bytes);
+        if (it < 1) it = 1;
+        // keep the CTA's stages within the SM's shared memory
+        const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
+        while (it > 1 && (it * step > MAX_TILE_ROWS || (it * step + 2) * row_bytes + 144 > budget)) --it;
+        T = it * step;
+        plan->T = (int)T;
+        plan->K = 0;
+        plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
     } else {
-        T = 5632 / row_bytes - 2;                // ~5.5 KB of DAP per tile: 16 warps per SM
-    }
-    if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
-    if ((T + 2) * row_bytes + 64 > stage_budget) T = (stage_budget - 64) / row_bytes - 2;
-    if (T < 1) T = 1;
-    plan->T = (int)T;
-    set_scan_shape(C, plan->T, &plan->geo);
-    plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 64), 128);
-    if (opts && opts->emit_buf_records > 0) {
-        plan->K = opts->emit_buf_records;
-    } else {
-        long long k = (T * C) / (16ll * groups);  // ~10x the HPRC-shaped density
-        if (k < 8) k = 8;
-        if (k > 128) k = 128;
-        plan->K = (int)k;
+        // a stage holds T + 2 rows; keep a warp's stages within its share of the SM
+        const long long stage_budget = (200 * 1024 / plan->warps - 1536) / plan->stages;
+        if (opts && opts->rows_per_tile > 0) {
+            T = opts->rows_per_tile;
+        } else {
+            T = 5632 / row_bytes - 2;                // ~5.5 KB of DAP per tile: 16 warps per SM
+        }
+        if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
+        if ((T + 2) * row_bytes + 64 > stage_budget) T = (stage_budget - 64) / row_bytes - 2;
+        if (T < 1) T = 1;
+        plan->T = (int)T;
+        set_scan_shape(C, plan->T, &plan->geo);
+        plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 64), 128);
+        if (opts && opts->emit_buf_records > 0) {
+            plan->K = opts->emit_buf_records;
+        } else {
+            long long k = (T * C) / (16ll * groups);  // ~10x the HPRC-shaped density
+            if (k < 8) k = 8;
+            if (k > 128) k = 128;
+            plan->K = (int)k;
+        }
     }
     size_t o = (size_t)plan->stages * plan->stage_bytes;
     plan->off_bars = (uint32_t)o;    o += 8 * MAX_STAGES;
@@ -755,8 +686,16 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
                      "segment %d: positions exceed int32", i);
         prev_end = s.row_begin + s.n_rows;
         if (tstart_host) tstart_host[i] = t;
-        const long long m = s.n_rows - ((s.flags & MEMO_SEG_PRIMED) ? 1 : 0);
-        const long long nt = (m + T - 1) / T;
+        const long long primed = (s.flags & MEMO_SEG_PRIMED) ? 1 : 0;
+        long long nt;
+        if (plan->narrow) {
+            // tiles start at multiples of rpl buffer rows (16-byte aligned bases)
+            const long long fc = s.row_begin + primed, lc = s.row_begin + s.n_rows - 1;
+            const long long g = ((fc - 1) / plan->rpl) * plan->rpl;
+            nt = lc >= fc ? (lc - g + T - 1) / T : 0;
+        } else {
+            nt = (s.n_rows - primed + T - 1) / T;
+        }
         t += nt > 0 ? nt : 1;
     }
     if (tstart_host) tstart_host[n_seg] = t;
@@ -852,7 +791,8 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(ws + plan.off_partial);
     P.result = result;
 
-    stream_kernel_t kern = select_kernel(plan.geo, order, n_cols, ld);
+    stream_kernel_t kern = plan.narrow ? select_narrow_kernel(n_cols, order, nullptr)
+                                       : select_kernel(plan.geo, order, n_cols, ld);
     if (!kern) {
         set_error("no kernel for KPL=%d", plan.geo.KPL);
         return MEMO_ERR_UNSUPPORTED;

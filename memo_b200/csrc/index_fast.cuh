@@ -1,0 +1,101 @@
+// Shared pieces of the single-pass index build (index_build.cu: generic warp-stream
+// kernel, scan, gather, host plan; index_narrow.cu: the lane-per-row kernel for
+// narrow DAP rows).
+#pragma once
+#include "common.cuh"
+
+namespace memo {
+namespace {
+
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_TILE_ROWS = 960;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gather block
+
+struct TileDesc {
+    int n;              // compare rows 1..n (row 0 of the tile is the predecessor row)
+    int off;            // word offset of row 0 inside the stage data
+    uint32_t pos_h;     // record-relative position of row 0
+    uint32_t rec_len;
+    int flags;          // 1 = last tile of its run, 2 = chr-end rows follow the run
+    int r_lo, r_hi;     // narrow kernel: live compare rows of the tile are r_lo..r_hi (1-based)
+    int pad;
+};
+
+struct FastParams {
+    const int32_t* dap;
+    long long total_bytes;             // rows * ld * 4
+    int32_t C;
+    int32_t ld;
+    const memo_segment_t* segs;        // device copy
+    const long long* seg_tile_start;   // device [n_seg + 1]
+    int32_t n_seg;
+    long long n_tiles;
+    int32_t T;                         // compare rows per tile
+    int32_t K;                         // staged index rows per group
+    int32_t stages;
+    uint32_t stage_bytes;
+    uint32_t warp_smem;                // shared-memory bytes per warp
+    uint32_t off_bars, off_descs, off_stg, off_list;   // inside the warp's region
+    int32_t gw;                        // phase B: lanes per row group (KPL == 1)
+    int32_t all_pairs;                 // phase B: all-pairs counting (narrow rows)
+    int32_t sl, wcols, rb;             // phase A: lanes per row, columns per lane, rows per lane
+    uint32_t* scr_start;               // scratch index rows (unordered tile blocks)
+    uint32_t* scr_end;
+    uint32_t* scr_order;
+    long long out_cap;
+    uint32_t* tile_cnt;                // [n_tiles]
+    unsigned long long* tile_off;      // [n_tiles] scratch offset of the tile's block
+    unsigned long long* cursor;        // scratch allocation cursor
+    int64_t* result;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+
+typedef void (*stream_kernel_t)(const FastParams);
+
+}  // namespace
+
+// index_narrow.cu: kernel for n_cols == ld == CT (compile-time) rows, or nullptr.
+// *rows_per_lane receives the number of consecutive rows a lane scans per step
+// (tile bases must be multiples of it so that they are 16-byte aligned).
+stream_kernel_t select_narrow_kernel(int n_cols, bool order, int* rows_per_lane);
+
+}  // namespace memo

@@ -1,0 +1,309 @@
+// DAP -> MEMO index rows on sm_100a: single-pass build for NARROW rows
+// (n_cols == ld == CT known at compile time, CT <= 16 -- the 5- and 10-genome
+// configurations), one lane per DAP row.
+//
+// Replaces the hot loop of the reference's src/dap_to_bed.py (--mem --overlap
+// [--order]): get_new_record :85-91, dap_to_mem :116-134, print_interval /
+// overlaps :93-109.  Same mathematics as index_build.cu (DESIGN.md "index
+// build"): with E[r][c] = p(r) + v[r][c] and A[r] = E[r] sorted descending
+// (--order) or E[r] itself, row r emits (p, A[r-1][j], j+1) for every j with
+// A[r][j] > A[r-1][j] and A[r-1][j] >= p, provided no E decreases down a column
+// (matching statistics).  Only rows in which some E moved can emit.
+//
+// Every warp is an independent stream over its own tiles (tile = T consecutive
+// rows + the predecessor row, fetched by one bulk async copy into the warp's
+// private multi-stage shared-memory ring).  Tile bases are multiples of RPL rows
+// of the buffer, which makes them 16-byte aligned, so that
+//   phase A  a lane scans RPL consecutive rows with 128-bit shared-memory loads
+//            (lane stride RPL*CT*4 bytes = an odd number of 16-byte units: no
+//            bank conflicts) and flags the rows where v[r][c] != v[r-1][c] - 1,
+//   phase B  one lane per flagged row sorts the row and its predecessor with a
+//            register sorting network (--order), compares them position by
+//            position and stores the index rows straight into the tile's block
+//            of the scratch area (block obtained with one atomicAdd per tile;
+//            tile_scan_kernel / tile_gather_kernel of index_build.cu order the
+//            blocks afterwards).
+// No warp ever waits for another.
+#include "index_fast.cuh"
+
+namespace memo {
+namespace {
+
+__host__ __device__ constexpr int gcd4(int c) { return (c % 4 == 0) ? 4 : ((c % 2 == 0) ? 2 : 1); }
+
+// Batcher odd-even merge sort network on P = 2^ceil(log2 N) wires with every
+// comparator touching a wire >= N removed (the missing wires would hold -inf and
+// sort to the end of a descending order anyway).
+template <int N>
+__device__ __forceinline__ void sort_desc_network(uint32_t (&a)[N]) {
+    constexpr int P = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : 16;
+#pragma unroll
+    for (int p = 1; p < P; p <<= 1) {
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1) {
+#pragma unroll
+            for (int j = k % p; j + k < P; j += 2 * k) {
+#pragma unroll
+                for (int i = 0; i < k; ++i) {
+                    const int x = i + j, y = i + j + k;
+                    if (y < N && (x / (2 * p)) == (y / (2 * p))) {
+                        const uint32_t hi = max(a[x], a[y]);
+                        const uint32_t lo = min(a[x], a[y]);
+                        a[x] = hi;
+                        a[y] = lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int CT, bool ORDER>
+__global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
+    constexpr int RPL = 4 / gcd4(CT);             // rows per lane per step
+    constexpr int RI = 32 * RPL;                  // rows per warp step
+    constexpr int NW = (RPL + 1) * CT;            // words a lane needs per step
+    constexpr int NV = (NW + 3) / 4;              // ... as 128-bit loads
+    static_assert(CT >= 1 && CT <= 16, "narrow rows only");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int S = P.stages, T = P.T;
+
+    unsigned char* const wbase = smem_raw + (size_t)warp * P.warp_smem;
+    uint64_t* const bars = (uint64_t*)(wbase + P.off_bars);
+    TileDesc* const descs = (TileDesc*)(wbase + P.off_descs);
+    uint16_t* const list = (uint16_t*)(wbase + P.off_list);
+
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long w_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+
+    // fetch tile `tile` into stage s (lane 0 only); the record run of the previous
+    // tile is kept in registers, consecutive tiles of a warp mostly share it
+    long long c_lo = 0, c_hi = 0;
+    memo_segment_t seg;
+    seg.row_begin = seg.n_rows = 0;
+    seg.pos0 = seg.rec_len = seg.rec_id = seg.flags = 0;
+    auto issue = [&](int s, long long tile) {
+        uint64_t* bar = &bars[s];
+        if (tile >= P.n_tiles) return;
+        if (tile < c_lo || tile >= c_hi) {
+            int s_lo = 0, s_hi = P.n_seg - 1;
+            while (s_lo < s_hi) {
+                const int mid = (s_lo + s_hi + 1) >> 1;
+                if (P.seg_tile_start[mid] <= tile) s_lo = mid; else s_hi = mid - 1;
+            }
+            c_lo = P.seg_tile_start[s_lo];
+            c_hi = P.seg_tile_start[s_lo + 1];
+            seg = P.segs[s_lo];
+        }
+        const long long t = tile - c_lo;
+        const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
+        const long long fc = seg.row_begin + primed;              // first / last compare row (buffer rows)
+        const long long lc = seg.row_begin + seg.n_rows - 1;
+        const long long g = ((fc - 1) / RPL) * RPL;               // aligned base of the run's first tile
+        const long long B = g + t * T;                            // buffer row of the tile's row 0
+        const long long lo = (fc > B + 1 ? fc : B + 1) - B;
+        const long long hi = (lc < B + T ? lc : B + T) - B;
+        const long long a0 = B * (long long)CT * 4;               // 16-byte aligned
+        long long end = (B + T + 1) * (long long)CT * 4;
+        if (end > P.total_bytes) end = P.total_bytes;
+        long long a1 = (end + 15) & ~15ll;
+        const long long lim = P.total_bytes & ~15ll;
+        if (a1 > lim) a1 = lim;
+        TileDesc d;
+        d.n = T;
+        d.off = 0;
+        d.pos_h = (uint32_t)seg.pos0 + (uint32_t)(B - seg.row_begin);
+        d.rec_len = (uint32_t)seg.rec_len;
+        d.flags = ((tile + 1 == c_hi) ? 1 : 0) | ((seg.flags & MEMO_SEG_CHR_END) ? 2 : 0);
+        d.r_lo = (int)lo;
+        d.r_hi = (int)hi;
+        d.pad = (int)(lc - B);                                    // tile row of the run's last row
+        descs[s] = d;
+        unsigned char* data = wbase + (size_t)s * P.stage_bytes;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.dap);
+        // the last < 16 bytes of the buffer cannot be part of a 16-byte granular bulk copy
+        for (long long b = a1; b < end; b += 4)
+            *reinterpret_cast<uint32_t*>(data + (b - a0)) = *reinterpret_cast<const uint32_t*>(src + b);
+        if (a1 > a0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));
+            bulk_g2s(data, src + a0, (uint32_t)(a1 - a0), bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int s = 0; s < S; ++s) issue(s, w_global + (long long)s * n_warps);
+
+    uint32_t irr_acc = 0;
+    int s = 0;
+    uint32_t parity = 0;
+
+    for (long long tile = w_global; tile < P.n_tiles; tile += n_warps) {
+        mbar_wait(&bars[s], parity);
+        const TileDesc d = descs[s];
+        const uint32_t* const sdata = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes);
+
+        // ---------------- phase A: ordered list of the live rows that moved a MEM end
+        int n_ch = 0;
+        for (int r0 = 0; r0 < T; r0 += RI) {
+            const int row0 = r0 + lane * RPL;                 // predecessor of the lane's first row
+            uint32_t acc[RPL];
+            if (row0 < d.r_hi && row0 + RPL >= d.r_lo) {
+                const uint4* src = reinterpret_cast<const uint4*>(sdata + row0 * CT);
+                uint32_t w[NV * 4];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const uint4 x = src[v];
+                    w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+                }
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    uint32_t a = 0;
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) a |= w[(q + 1) * CT + c] + 1u - w[q * CT + c];
+                    const int row = row0 + 1 + q;
+                    acc[q] = (row >= d.r_lo && row <= d.r_hi) ? a : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) acc[q] = 0u;
+            }
+            unsigned bal[RPL];
+            unsigned any = 0;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                irr_acc |= acc[q];
+                bal[q] = __ballot_sync(FULL, acc[q] != 0u);
+                any |= bal[q];
+            }
+            if (any) {
+                // list order = row order = (lane, q) lexicographic
+                int o = n_ch, total = 0;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    o += __popc(bal[q] & ltmask);
+                    total += __popc(bal[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < RPL; ++q)
+                    if (acc[q] != 0u) list[o++] = (uint16_t)(row0 + 1 + q);
+                n_ch += total;
+            }
+        }
+        if ((d.flags & 3) == 3) {                       // the chr-end rows after the run's last row
+            if (lane == 0) list[n_ch] = (uint16_t)(0x8000 | (d.pad + 1));
+            ++n_ch;
+        }
+        __syncwarp();
+
+        // ---------------- phase B: one lane per listed row
+        // e[] = (sorted) MEM ends of the predecessor row; returns the bitmap of the
+        // sorted positions / columns that emit an index row
+        auto row_rows = [&](int idx, uint32_t (&e)[CT], uint32_t& p, uint32_t& lim) -> unsigned {
+            const bool act = idx < n_ch;
+            const unsigned ent = act ? list[idx] : 1u;
+            const bool chr = (ent & 0x8000u) != 0u;
+            const int row = (int)(ent & 0x7FFFu);
+            const uint32_t* prevp = sdata + (row - 1) * CT;
+            const uint32_t ppos = d.pos_h + (uint32_t)(row - 1);
+            p = chr ? d.rec_len : ppos + 1u;
+            lim = chr ? 2u * d.rec_len : 0xFFFFFFFFu;
+            uint32_t f[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                e[c] = prevp[c] + ppos;
+                f[c] = chr ? 0xFFFFFFFFu : prevp[CT + c] + ppos + 1u;
+            }
+            if (ORDER) {
+                sort_desc_network<CT>(e);
+                sort_desc_network<CT>(f);
+            }
+            unsigned m = 0;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) m |= (f[c] > e[c] && e[c] >= p) ? (1u << c) : 0u;
+            return act ? m : 0u;
+        };
+
+        const int n_pass = (n_ch + 31) >> 5;
+        unsigned long long base = 0;
+        uint32_t tile_total = 0;
+        if (n_pass > 1) {                               // dense tile: count first, the block must be contiguous
+            uint32_t cnt = 0;
+            for (int ps = 0; ps < n_pass; ++ps) {
+                uint32_t e[CT], p, lim;
+                cnt += __popc(row_rows(ps * 32 + lane, e, p, lim));
+            }
+            tile_total = __reduce_add_sync(FULL, cnt);
+            if (lane == 0 && tile_total) base = atomicAdd(P.cursor, (unsigned long long)tile_total);
+            base = __shfl_sync(FULL, base, 0);
+        }
+        uint32_t running = 0;
+        for (int ps = 0; ps < n_pass; ++ps) {
+            uint32_t e[CT], p, lim;
+            const unsigned m = row_rows(ps * 32 + lane, e, p, lim);
+            const uint32_t cnt = __popc(m);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (n_pass == 1) {
+                tile_total = total;
+                if (lane == 0 && total) base = atomicAdd(P.cursor, (unsigned long long)total);
+                base = __shfl_sync(FULL, base, 0);
+            }
+            unsigned long long gi = base + running + (incl - cnt);
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                if (m & (1u << c)) {
+                    if (gi < (unsigned long long)P.out_cap) {
+                        P.scr_start[gi] = p;
+                        P.scr_end[gi] = min(e[c], lim);
+                        P.scr_order[gi] = (uint32_t)(c + 1);
+                    }
+                    ++gi;
+                }
+            }
+            running += total;
+        }
+        if (lane == 0) {
+            P.tile_cnt[tile] = tile_total;
+            P.tile_off[tile] = base;
+        }
+        __syncwarp();                    // stage s and the list are free again
+        if (lane == 0) issue(s, tile + (long long)S * n_warps);
+        if (++s == S) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+    if (irr_acc >> 31) P.result[MEMO_RES_IRREGULAR] = 1;
+}
+
+}  // namespace
+
+stream_kernel_t select_narrow_kernel(int n_cols, bool order, int* rows_per_lane) {
+#define MEMO_NARROW(CC)                                                            \
+    if (n_cols == CC) {                                                            \
+        if (rows_per_lane) *rows_per_lane = 4 / gcd4(CC);                          \
+        return order ? narrow_kernel<CC, true> : narrow_kernel<CC, false>;         \
+    }
+    MEMO_NARROW(4) MEMO_NARROW(9)
+#undef MEMO_NARROW
+    return nullptr;
+}
+
+}  // namespace memo

@@ -154,6 +154,43 @@ def test_index_multi_record_and_partial(order):
     assert not res.general
 
 
+@pytest.mark.parametrize("C", [4, 9])
+@pytest.mark.parametrize("order", [True, False])
+def test_index_narrow_kernel_shapes(C, order):
+    """Lane-per-row kernel (index_narrow.cu): aligned tile bases vs arbitrary run
+    starts, one-row records, dense tiles (several passes), tile sizes, and the
+    generic warp-stream kernel on the same input."""
+    lens = [1, 5000, 2, 1, 3, 12001, 300, 7777, 1]
+    recs = [(f"c{i}", n) for i, n in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=300 + i, dense=(i % 2 == 1))
+                           for i, n in enumerate(lens)])
+    want = mo.index_build(vals, recs, order)
+    for kw in ({}, {"rows_per_tile": 1}, {"rows_per_tile": 512}, {"rows_per_tile": 900, "stages": 1, "warps_per_cta": 4},
+               {"stages": 4, "warps_per_cta": 3}, {"kernel_variant": 1}):
+        res, got = gpu_index(vals, recs, order, **kw)
+        assert_index_equal(got, want, f"narrow C={C} order={order} {kw}")
+        assert not res.general
+
+
+@pytest.mark.parametrize("C", [4, 9])
+@pytest.mark.parametrize("shift", [1, 2, 3, 4, 7])
+def test_index_narrow_kernel_position_shards(C, shift):
+    """A position shard: the buffer starts `shift` rows before the owned rows (row
+    shift-1 is the halo), the run continues a record and is continued by another
+    shard (no chr-end rows), followed by halo rows that belong to nobody."""
+    api = _api()
+    L = 9000
+    vals = mo.synth_dap(L, C, seed=77 + C, dense=True)
+    whole = mo.index_build(vals, [("chrS", L)], True)
+    lo, hi = 2500, 7013
+    buf = torch.from_numpy(np.ascontiguousarray(vals[lo - shift:hi + 50], dtype=np.int32)).cuda()
+    segs = [api.Segment(row_begin=shift, n_rows=hi - lo, pos0=lo, rec_len=L, rec_id=0, flags=0)]
+    res = api.IndexBuilder().build(buf, C, segs, True)
+    got = res.to_host()
+    keep = (whole[1] >= lo) & (whole[1] < hi)
+    assert_index_equal(got, tuple(w[keep] for w in whole), f"shard shift={shift}")
+
+
 def test_index_position_beyond_records_raises():
     api = _api()
     dap = torch.zeros((10, 2), dtype=torch.int32, device="cuda")
