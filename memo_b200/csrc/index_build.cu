@@ -475,7 +475,7 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
                    const uint32_t* __restrict__ scr_start, const uint32_t* __restrict__ scr_end,
                    const uint32_t* __restrict__ scr_order, int32_t* __restrict__ out_start,
                    uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                   int64_t* __restrict__ seg_out_end) {
+                   long long scr_cap, int64_t* __restrict__ seg_out_end) {
     __shared__ uint32_t excl[SCAN_BLOCK];          // exclusive row offset of each tile in the block
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
@@ -549,7 +549,7 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
             if (i < tot) {
                 const unsigned long long src = ooff + (i - orel);
                 const unsigned long long dst = base + first + i;
-                if (src < (unsigned long long)out_cap && dst < (unsigned long long)out_cap) {
+                if (src < (unsigned long long)scr_cap && dst < (unsigned long long)out_cap) {
                     out_start[dst] = (int32_t)scr_start[src];
                     out_end[dst] = scr_end[src];
                     out_order[dst] = (int32_t)scr_order[src];
@@ -600,6 +600,8 @@ struct FastPlan {
     Geometry geo;
     int narrow, rpl;            // lane-per-row kernel (index_narrow.cu) and its rows per lane
     int T, K, stages, warps, ctas_per_sm;
+    uint32_t chunk;             // scratch rows per warp reservation
+    long long scr_cap;          // entries per scratch array
     uint32_t stage_bytes, warp_smem, off_bars, off_descs, off_stg, off_list;
     long long n_tiles, n_blocks;
     size_t smem;
@@ -632,7 +634,7 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         // whole warp steps of 32 * rpl rows, ~4.5-9 KB of DAP per tile
         const long long step = 32ll * plan->rpl;
         long long it = (opts && opts->rows_per_tile > 0) ? (opts->rows_per_tile + step - 1) / step
-                                                          : (5632 + step * row_bytes - 1) / (step * row_bytes);
+                                                          : (5632 + step * row_bytes / 2) / (step * row_bytes);
         if (it < 1) it = 1;
         // keep the CTA's stages within the SM's shared memory
         const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
@@ -667,7 +669,7 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     size_t o = (size_t)plan->stages * plan->stage_bytes;
     plan->off_bars = (uint32_t)o;    o += 8 * MAX_STAGES;
     plan->off_descs = (uint32_t)o;   o += sizeof(TileDesc) * MAX_STAGES;
-    plan->off_stg = (uint32_t)o;     o += 12 * (size_t)groups * plan->K;
+    plan->off_stg = (uint32_t)o;     o += plan->narrow ? 4 * 32 * (size_t)(C | 1) : 12 * (size_t)groups * plan->K;
     plan->off_list = (uint32_t)o;    o += 2 * (size_t)(T + 4);
     plan->warp_smem = (uint32_t)align_up(o, 128);
     plan->smem = (size_t)plan->warp_smem * plan->warps;
@@ -708,7 +710,15 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_off = off;     off = align_up(off + 8 * (size_t)(t > 0 ? t : 1), 256);
     plan->off_partial = off; off = align_up(off + 8 * (size_t)(plan->n_blocks > 0 ? plan->n_blocks : 1), 256);
     plan->off_ctrl = off;    off = align_up(off + 256, 256);
-    plan->off_scratch = off; off = align_up(off + 12 * (size_t)out_cap + 48, 256);
+    // scratch: warps reserve it in chunks (warp_alloc), which wastes < 1/4 of every
+    // chunk plus each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice
+    const long long max_warps = (long long)device_sm_count() * 32;
+    long long chunk = 4096;
+    while (chunk > 256 && chunk * max_warps * 8 > out_cap) chunk >>= 1;
+    while (chunk < 4ll * C) chunk <<= 1;
+    plan->chunk = (uint32_t)chunk;
+    plan->scr_cap = out_cap > 0 ? ((out_cap + max_warps * chunk) * 4 / 3 + 64) & ~3ll : 0;
+    plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
     plan->total = off;
     return MEMO_OK;
 }
@@ -781,9 +791,9 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.gw = plan.geo.gw; P.all_pairs = plan.geo.all_pairs; P.sl = plan.geo.sl; P.wcols = plan.geo.wcols; P.rb = plan.geo.rb;
     P.off_stg = plan.off_stg; P.off_list = plan.off_list;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(ws + plan.off_scratch);
-    const size_t cap4 = ((size_t)out_cap + 3) & ~(size_t)3;
+    const size_t cap4 = (size_t)plan.scr_cap;
     P.scr_start = scratch; P.scr_end = scratch + cap4; P.scr_order = scratch + 2 * cap4;
-    P.out_cap = out_cap;
+    P.out_cap = out_cap; P.scr_cap = plan.scr_cap; P.chunk = plan.chunk;
     P.tile_cnt = reinterpret_cast<uint32_t*>(ws + plan.off_cnt);
     P.tile_off = reinterpret_cast<unsigned long long*>(ws + plan.off_off);
     P.cursor = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl);
@@ -818,7 +828,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     MEMO_CUDA_TRY(cudaGetLastError());
     tile_gather_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(
         P.tile_cnt, P.tile_off, plan.n_tiles, partial, P.seg_tile_start, n_seg, P.scr_start, P.scr_end,
-        P.scr_order, out_start, out_end, out_order, out_cap, seg_out_end);
+        P.scr_order, out_start, out_end, out_order, out_cap, plan.scr_cap, seg_out_end);
     MEMO_CUDA_TRY(cudaGetLastError());
     return MEMO_OK;
 }

@@ -44,7 +44,9 @@ struct FastParams {
     uint32_t* scr_start;               // scratch index rows (unordered tile blocks)
     uint32_t* scr_end;
     uint32_t* scr_order;
-    long long out_cap;
+    long long out_cap;                 // 0 = count only
+    long long scr_cap;                 // entries per scratch array
+    uint32_t chunk;                    // scratch rows a warp reserves per atomicAdd
     uint32_t* tile_cnt;                // [n_tiles]
     unsigned long long* tile_off;      // [n_tiles] scratch offset of the tile's block
     unsigned long long* cursor;        // scratch allocation cursor
@@ -88,6 +90,32 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+
+// Scratch allocation.  A warp reserves P.chunk rows of the scratch area with one
+// atomicAdd and hands them out locally ([w_cur, w_end), warp uniform), so that the
+// single allocation cursor sees one atomic per few hundred tiles instead of one
+// per tile.  A request that does not fit the rest of the chunk takes a fresh
+// chunk (the rest is abandoned: < chunk/4 rows) or, when it is large itself, an
+// exactly sized reservation.  Returns the first row of a contiguous block of
+// `total` rows; warp uniform.
+__device__ __forceinline__ unsigned long long warp_alloc(const FastParams& P, unsigned long long& w_cur,
+                                                         unsigned long long& w_end, uint32_t total,
+                                                         int lane) {
+    if (total <= w_end - w_cur) {
+        const unsigned long long base = w_cur;
+        w_cur += total;
+        return base;
+    }
+    const bool big = total > P.chunk / 4;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.cursor, (unsigned long long)(big ? total : P.chunk));
+    base = __shfl_sync(FULL, base, 0);
+    if (!big) {
+        w_cur = base + total;
+        w_end = base + P.chunk;
+    }
+    return base;
+}
 
 typedef void (*stream_kernel_t)(const FastParams);
 

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     uint32_t irr_acc = 0;
     int s = 0;
     uint32_t parity = 0;
+    unsigned long long w_cur = 0, w_end = 0;          // the warp's reserved scratch rows
+    uint32_t* const ecol = reinterpret_cast<uint32_t*>(wbase + P.off_stg) + lane * (CT | 1);
 
     for (long long tile = w_global; tile < P.n_tiles; tile += n_warps) {
         mbar_wait(&bars[s], parity);
@@ -245,8 +247,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
                 cnt += __popc(row_rows(ps * 32 + lane, e, p, lim));
             }
             tile_total = __reduce_add_sync(FULL, cnt);
-            if (lane == 0 && tile_total) base = atomicAdd(P.cursor, (unsigned long long)tile_total);
-            base = __shfl_sync(FULL, base, 0);
+            if (tile_total) base = warp_alloc(P, w_cur, w_end, tile_total, lane);
         }
         uint32_t running = 0;
         for (int ps = 0; ps < n_pass; ++ps) {
@@ -262,20 +263,22 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
             const uint32_t total = __shfl_sync(FULL, incl, 31);
             if (n_pass == 1) {
                 tile_total = total;
-                if (lane == 0 && total) base = atomicAdd(P.cursor, (unsigned long long)total);
-                base = __shfl_sync(FULL, base, 0);
+                if (total) base = warp_alloc(P, w_cur, w_end, total, lane);
             }
+            // the lane's index rows: its emitting positions in ascending order.  The
+            // (sorted) ends go through the lane's shared-memory column so that the loop
+            // runs once per emitted row, not once per column.
             unsigned long long gi = base + running + (incl - cnt);
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                if (m & (1u << c)) {
-                    if (gi < (unsigned long long)P.out_cap) {
-                        P.scr_start[gi] = p;
-                        P.scr_end[gi] = min(e[c], lim);
-                        P.scr_order[gi] = (uint32_t)(c + 1);
-                    }
-                    ++gi;
-                }
+            for (int c = 0; c < CT; ++c) ecol[c] = min(e[c], lim);
+            unsigned mm = (gi + cnt <= (unsigned long long)P.scr_cap) ? m : 0u;
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                P.scr_start[gi] = p;
+                P.scr_end[gi] = ecol[c];
+                P.scr_order[gi] = (uint32_t)(c + 1);
+                ++gi;
             }
             running += total;
         }
