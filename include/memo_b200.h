@@ -58,12 +58,13 @@ typedef struct memo_segment {
 
 typedef struct memo_index_opts {
     int32_t order_mode;       /* 1 = --order (conservation), 0 = membership */
-    int32_t rows_per_tile;    /* DAP rows per shared-memory tile (general build: per strip), 0 = default */
-    int32_t emit_buf_records; /* index rows staged in shared memory per lane group, 0 = default */
+    int32_t rows_per_tile;    /* DAP rows per shared-memory stage (general build: per strip), 0 = default */
+    int32_t emit_buf_records; /* wide rows: DAP rows per strip (general build: index rows staged per
+                                 lane group), 0 = default */
     int32_t warps_per_cta;    /* 0 = default (8) */
     int32_t ctas_per_sm;      /* cap on resident CTAs per SM, 0 = as many as fit */
-    int32_t stages;           /* bulk-copy pipeline depth per CTA, 0 = default (2), max 4 */
-    int32_t kernel_variant;   /* 0 = pick, 1 = force the generic warp-stream kernel (tests) */
+    int32_t stages;           /* bulk-copy pipeline depth per warp, 0 = default (2), max 4 */
+    int32_t kernel_variant;   /* 0 = pick, 1 = force the strip kernel for narrow rows too (tests) */
     int32_t reserved;
 } memo_index_opts_t;
 
@@ -72,7 +73,7 @@ typedef struct memo_index_opts {
 #define MEMO_RES_IRREGULAR 1 /* != 0: input is not valid matching statistics;
                                 the fast build's output must be discarded and
                                 memo_index_build_general run instead */
-#define MEMO_RES_REPLAYS 2   /* tiles whose staging buffer overflowed (stat) */
+#define MEMO_RES_REPLAYS 2   /* general build: strips whose staging buffer overflowed (stat) */
 #define MEMO_RES_SLOTS 4
 
 int memo_abi_version(void);

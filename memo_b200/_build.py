@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmemo_b200.so")
-SOURCES = ["abi.cu", "index_build.cu", "index_narrow.cu", "index_general.cu", "query.cu", "synth.cu", "format.cu"]
+SOURCES = ["abi.cu", "index_build.cu", "index_narrow.cu", "index_wide.cu", "index_general.cu", "query.cu", "synth.cu", "format.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-cudart", "static",
@@ -35,7 +35,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link libmemo_b200.so.  Returns its path."""
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "index_fast.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "index_fast.cuh"), os.path.join(CSRC, "warp_sort.cuh"),
                os.path.join(os.path.dirname(HERE), "include", "memo_b200.h")]
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs, jobs = [], []

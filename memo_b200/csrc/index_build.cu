@@ -1,4 +1,6 @@
-// DAP -> MEMO index rows on sm_100a: the single-pass build for matching statistics.
+// DAP -> MEMO index rows on sm_100a: the single-pass build for matching statistics
+// (host plan, scan and gather kernels; the streaming kernels live in
+// index_narrow.cu and index_wide.cu).
 //
 // Replaces the hot loop of the reference's src/dap_to_bed.py (--mem --overlap
 // [--order]): get_new_record :85-91, dap_to_mem :116-134, print_interval /
@@ -13,31 +15,20 @@
 //   but its predecessor, and rows with E[r] == E[r-1] (the vast majority: E
 //   only moves where a new MEM starts) emit nothing.
 //
-// In --order mode no sort is run.  With G(v) = #{c : E[r-1][c] > v} and
-// D(v) = #{c : E[r-1][c] <= v < E[r][c]} (columns whose MEM end crossed v), the
-// sorted positions that change are, for every value v of the previous row with
-// D(v) > 0, the first min(D(v), multiplicity(v)) positions holding v:
-// j = G(v) + t.  A changed row costs counting proportional to the index rows it
-// emits, not a sort.
-//
-// Three kernels:
-//  1 stream_kernel  every warp is an independent stream over its own tiles
-//      (tile = T consecutive rows of one record run + the predecessor row,
-//      tiles dealt round-robin to warps).  A tile is fetched into the warp's
-//      private shared-memory stage by one bulk async copy (TMA: cp.async.bulk +
-//      mbarrier, multi-stage), then
-//        phase A  flat 128-bit scan for cells with v[r][c] != v[r-1][c] - 1
-//                 -> bitmap of changed rows (and the "irregular" verdict when a
-//                 MEM end decreases),
-//        phase B  groups of G lanes turn the changed rows into index rows,
-//                 staged in shared memory,
-//      and the tile's rows are appended to a scratch area at a block obtained by
-//      one atomicAdd (unordered, exactly sized).  No warp ever waits for another.
-//  2 tile_scan_kernel   block sums of the per-tile row counts; the last block to
-//      finish scans the block sums.
-//  3 tile_gather_kernel exclusive scan inside each block of tiles and copy of
-//      every tile's rows from its scratch block to its place in the ordered
-//      output (the extra traffic is 24 B per index row, a few % of the DAP).
+// Three kernels per build:
+//  1 a streaming kernel reads the DAP exactly once (bulk async copies into
+//    per-warp shared-memory rings; warps never wait for each other) and appends
+//    the index rows of its work units to a scratch area, unordered:
+//      narrow_kernel  n_cols <= 16: unit = tile of T rows, one lane per row
+//      wide_kernel    otherwise:    unit = strip of R rows, one warp per strip,
+//                     sorted row kept in registers and updated incrementally
+//    Every unit owns `mult` slots of tile_cnt / tile_off describing the blocks
+//    of scratch rows it wrote.
+//  2 tile_scan_kernel   block sums of the slot counts; the last block to finish
+//    scans the block sums.
+//  3 tile_gather_kernel exclusive scan inside each block of slots and copy of
+//    every block from the scratch area to its place in the ordered output (the
+//    extra traffic is 24 B per index row, a few % of the DAP).
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in
 // result[MEMO_RES_IRREGULAR].
@@ -46,375 +37,7 @@
 namespace memo {
 namespace {
 
-// ---------------------------------------------------------------- kernel 1
-// KPL = DAP columns per lane in phase B (1: a row is handled by a group of
-// P.gw lanes and several rows share a warp; > 1: one warp per row).
-// CT = compile-time number of DAP columns with ld == CT and one lane per row in
-// phase A (0: generic): every loop over columns unrolls to immediate offsets.
-template <int KPL, bool ORDER, int CT>
-__global__ void __launch_bounds__(256) stream_kernel(const FastParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const unsigned ltmask = (1u << lane) - 1u;
-    const int C = CT ? CT : P.C, ld = CT ? CT : P.ld, K = P.K, S = P.stages;
-    // phase B geometry: groups of GW lanes, RP rows per pass
-    const int GW = (KPL == 1) ? (CT ? (CT <= 16 ? CT : 32) : P.gw) : 32;
-    const int RP = 32 / GW;
-    const int g = lane / GW;
-    const int lg = lane - g * GW;
-    const bool glive = g < RP;
-    const unsigned gmask = !glive ? 0u : (GW == 32 ? FULL : (((1u << (GW & 31)) - 1u) << (g * GW)));
-    // phase A geometry: a row is scanned by SL lanes (SL a power of two), W columns each
-    const int SL = CT ? 1 : P.sl, W = CT ? CT : P.wcols;
-    const int RL = 32 / SL;
-    const int ar = lane / SL, sg = lane & (SL - 1);
-    const int a_c0 = sg * W;
-    const int a_cw = min(W, C - a_c0);
-
-    // the warp's private shared memory
-    unsigned char* const wbase = smem_raw + (size_t)warp * P.warp_smem;
-    uint64_t* const bars = (uint64_t*)(wbase + P.off_bars);
-    TileDesc* const descs = (TileDesc*)(wbase + P.off_descs);
-    uint32_t* const stg = (uint32_t*)(wbase + P.off_stg) + (size_t)(glive ? g : 0) * K * 3;
-    uint16_t* const list = (uint16_t*)(wbase + P.off_list);
-
-    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long w_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-
-    // fetch tile `tile` into stage s (lane 0 only); the record run of the previous
-    // tile is kept in registers, consecutive tiles of a warp mostly share it
-    long long c_lo = 0, c_hi = 0;
-    memo_segment_t seg;
-    seg.row_begin = seg.n_rows = 0;
-    seg.pos0 = seg.rec_len = seg.rec_id = seg.flags = 0;
-    auto issue = [&](int s, long long tile) {
-        uint64_t* bar = &bars[s];
-        if (tile >= P.n_tiles) return;
-        if (tile < c_lo || tile >= c_hi) {
-            int s_lo = 0, s_hi = P.n_seg - 1;
-            while (s_lo < s_hi) {
-                const int mid = (s_lo + s_hi + 1) >> 1;
-                if (P.seg_tile_start[mid] <= tile) s_lo = mid; else s_hi = mid - 1;
-            }
-            c_lo = P.seg_tile_start[s_lo];
-            c_hi = P.seg_tile_start[s_lo + 1];
-            seg = P.segs[s_lo];
-        }
-        const long long t = tile - c_lo;
-        const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
-        const long long m = seg.n_rows - primed;                    // compare rows of the run
-        const long long h = seg.row_begin - (1 - primed) + t * P.T; // buffer row of the tile's row 0
-        long long n = m - t * P.T;
-        if (n > P.T) n = P.T;
-        if (n < 0) n = 0;
-        const long long start = h * (long long)ld * 4;
-        const long long end = (h + n) * (long long)ld * 4 + (long long)C * 4;
-        const long long a0 = start & ~15ll;
-        long long a1 = (end + 15) & ~15ll;
-        const long long lim = P.total_bytes & ~15ll;
-        if (a1 > lim) a1 = lim;
-        TileDesc d;
-        d.n = (int)n;
-        d.off = (int)((start - a0) >> 2);
-        d.pos_h = (uint32_t)(seg.pos0 - (1 - primed)) + (uint32_t)(t * P.T);
-        d.rec_len = (uint32_t)seg.rec_len;
-        d.flags = ((tile + 1 == c_hi) ? 1 : 0) | ((seg.flags & MEMO_SEG_CHR_END) ? 2 : 0);
-        d.r_lo = 1; d.r_hi = (int)n; d.pad = 0;
-        descs[s] = d;
-        unsigned char* data = wbase + (size_t)s * P.stage_bytes + 16;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.dap);
-        // the last < 16 bytes of the buffer cannot be part of a 16-byte granular bulk copy
-        for (long long b = a1; b < end; b += 4)
-            *reinterpret_cast<uint32_t*>(data + (b - a0)) = *reinterpret_cast<const uint32_t*>(src + b);
-        if (a1 > a0) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));
-            bulk_g2s(data, src + a0, (uint32_t)(a1 - a0), bar);
-        } else {
-            mbar_arrive(bar);
-        }
-    };
-
-    if (lane == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-    if (lane == 0)
-        for (int s = 0; s < S; ++s) issue(s, w_global + (long long)s * n_warps);
-
-    uint32_t irr_acc = 0;
-    unsigned long long replays = 0;
-    int s = 0;
-    uint32_t parity = 0;
-
-    for (long long tile = w_global; tile < P.n_tiles; tile += n_warps) {
-        mbar_wait(&bars[s], parity);
-        const TileDesc d = descs[s];
-        const int n = d.n, off = d.off;
-        const uint32_t* const sdata = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes + 16);
-
-        // ---------------- phase A: ordered list of the rows that moved a MEM end
-        // (v[r][c] + 1 - v[r-1][c] != 0 somewhere in the row).  32 / SL rows per step,
-        // SL lanes per row with W columns each.
-        int n_ch = 0;
-        for (int r0 = 1; r0 <= n; r0 += RL) {
-            const int row = r0 + ar;
-            uint32_t acc = 0;
-            if (row <= n && a_cw > 0) {
-                const uint32_t* cur = sdata + off + row * ld + a_c0;
-                const uint32_t* prv = cur - ld;
-                if (CT) {
-#pragma unroll
-                    for (int c = 0; c < CT; ++c) acc |= cur[c] + 1u - prv[c];
-                } else {
-#pragma unroll 4
-                    for (int c = 0; c < a_cw; ++c) acc |= cur[c] + 1u - prv[c];
-                }
-            }
-            for (int o = 1; o < SL; o <<= 1) acc |= __shfl_xor_sync(FULL, acc, o);
-            irr_acc |= acc;
-            const bool mine = acc != 0u && sg == 0;
-            const unsigned bal = __ballot_sync(FULL, mine);
-            if (bal) {
-                if (mine) list[n_ch + __popc(bal & ltmask)] = (uint16_t)row;
-                n_ch += __popc(bal);
-            }
-        }
-        if ((d.flags & 3) == 3) {                       // pseudo row n + 1: the chr-end rows
-            if (lane == 0) list[n_ch] = (uint16_t)(n + 1);
-            ++n_ch;
-        }
-        __syncwarp();
-        const int chunk = (n_ch + RP - 1) / RP;
-
-        // ---------------- phase B: index rows of the changed rows
-        uint32_t gcount = 0;
-        unsigned long long gbase = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool direct = pass == 1;
-            gcount = 0;
-            for (int ci = 0; ci < chunk; ++ci) {
-                const int idx = g * chunk + ci;
-                const bool act = glive && idx < n_ch;
-                const int row = act ? (int)list[idx] : 1;
-                const bool chr = act && row == n + 1;
-                const uint32_t* prevp = sdata + off + (row - 1) * ld;
-                const uint32_t ppos = d.pos_h + (uint32_t)(row - 1);
-                const uint32_t p = chr ? d.rec_len : ppos + 1u;
-                const uint32_t lim = chr ? 2u * d.rec_len : 0xFFFFFFFFu;
-                uint32_t e[KPL], f[KPL];
-                bool valid[KPL];
-#pragma unroll
-                for (int k = 0; k < KPL; ++k) {
-                    const int c = k * GW + lg;
-                    valid[k] = c < C && glive;
-                    e[k] = valid[k] ? prevp[c] + ppos : 0u;
-                    f[k] = valid[k] ? (chr ? 0xFFFFFFFFu : prevp[ld + c] + ppos + 1u) : 0u;
-                }
-                bool em[KPL];           // slot emits an index row
-                uint32_t jpos[KPL];     // its 0-based order / genome column
-                uint32_t rank[KPL];     // its rank among the row's index rows
-                uint32_t total = 0;
-
-                if (!ORDER) {
-                    unsigned bal[KPL];
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        em[k] = act && valid[k] && f[k] > e[k] && e[k] >= p;
-                        jpos[k] = (uint32_t)(k * GW + lg);
-                        bal[k] = __ballot_sync(FULL, em[k]) & gmask;
-                    }
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        rank[k] = total + __popc(bal[k] & ltmask);
-                        total += __popc(bal[k]);
-                    }
-                } else if (KPL == 1 && (CT ? CT <= 12 : P.all_pairs)) {
-                    // narrow rows.  D(v): one step per changed column of the row (lockstep
-                    // over the warp's groups); tie index t from a match on (group, v);
-                    // G(v) for every lane at once by all pairs within the group.
-                    uint32_t dd = chr ? 0x7FFFFFFFu : 0u;
-                    unsigned m = __ballot_sync(FULL, act && !chr && f[0] != e[0]) & gmask;
-                    while (__any_sync(FULL, m != 0u)) {
-                        const bool on = m != 0u;
-                        const int src = on ? __ffs(m) - 1 : lane;
-                        m &= m - 1;
-                        const uint32_t x = __shfl_sync(FULL, e[0], src);
-                        const uint32_t y = __shfl_sync(FULL, f[0], src);
-                        dd += (on && e[0] >= x && e[0] < y) ? 1u : 0u;
-                    }
-                    const bool cand = act && valid[0] && dd > 0u && e[0] >= p;
-                    uint32_t Gt = 0, tt = 0;
-                    if (__any_sync(FULL, cand)) {
-                        const int src0 = glive ? g * GW : 0;
-#pragma unroll
-                        for (int kk = 0; kk < (CT ? CT : 1); ++kk) {
-                            if (CT == 0) break;
-                            const uint32_t ek = __shfl_sync(FULL, e[0], src0 + kk);
-                            Gt += (ek > e[0]) ? 1u : 0u;
-                            tt += (ek == e[0] && kk < lg) ? 1u : 0u;
-                        }
-                        if (CT == 0) {
-                            for (int kk = 0; kk < C; ++kk) {
-                                const uint32_t ek = __shfl_sync(FULL, e[0], src0 + kk);
-                                Gt += (ek > e[0]) ? 1u : 0u;
-                                tt += (ek == e[0] && kk < lg) ? 1u : 0u;
-                            }
-                        }
-                    }
-                    em[0] = cand && tt < dd;
-                    jpos[0] = Gt + tt;
-                    const int sh = glive ? g * GW : 0;
-                    const unsigned all = __reduce_or_sync(FULL, em[0] ? (1u << ((sh + (int)jpos[0]) & 31)) : 0u);
-                    const unsigned mine = (all & gmask) >> sh;
-                    rank[0] = __popc(mine & ((1u << (jpos[0] & 31)) - 1u));
-                    total = __popc(mine);
-                } else {
-                    // crossings per slot: D(v) for v = this slot's previous MEM end.  The
-                    // loops run in lockstep over the warp's groups; `on` = my group still
-                    // has work in this step.
-                    uint32_t dcross[KPL];
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) dcross[k] = chr ? 0x7FFFFFFFu : 0u;
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        unsigned m = __ballot_sync(FULL, act && !chr && f[k] != e[k]) & gmask;
-                        while (__any_sync(FULL, m != 0u)) {
-                            const bool on = m != 0u;
-                            const int src = on ? __ffs(m) - 1 : lane;
-                            m &= m - 1;
-                            const uint32_t x = __shfl_sync(FULL, e[k], src);
-                            const uint32_t y = __shfl_sync(FULL, f[k], src);
-#pragma unroll
-                            for (int kk = 0; kk < KPL; ++kk)
-                                dcross[kk] += (on && e[kk] >= x && e[kk] < y) ? 1u : 0u;
-                        }
-                    }
-                    // one counting step per candidate value: G(v), tie index t
-                    uint32_t mw[KPL];   // bitmap of the sorted positions that emit (group uniform)
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        mw[k] = 0;
-                        em[k] = false;
-                        jpos[k] = 0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        unsigned m = __ballot_sync(FULL, act && valid[k] && dcross[k] > 0u && e[k] >= p) & gmask;
-                        while (__any_sync(FULL, m != 0u)) {
-                            const bool on = m != 0u;
-                            const int src = on ? __ffs(m) - 1 : lane;
-                            m &= m - 1;
-                            const uint32_t v = __shfl_sync(FULL, e[k], src);
-                            const uint32_t dsrc = __shfl_sync(FULL, dcross[k], src);
-                            uint32_t Gc = 0, tc = 0;
-#pragma unroll
-                            for (int kk = 0; kk < KPL; ++kk) {
-                                Gc += __popc(__ballot_sync(FULL, e[kk] > v) & gmask);
-                                if (kk <= k) {
-                                    const unsigned eq = __ballot_sync(FULL, e[kk] == v) & gmask;
-                                    tc += (kk < k) ? __popc(eq) : __popc(eq & ((1u << src) - 1u));
-                                }
-                            }
-                            if (on && tc < dsrc) {
-                                const uint32_t j = Gc + tc;
-                                if (lane == src) {
-                                    em[k] = true;
-                                    jpos[k] = j;
-                                }
-#pragma unroll
-                                for (int w = 0; w < KPL; ++w)
-                                    if ((int)(j >> 5) == w) mw[w] |= 1u << (j & 31);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        uint32_t r = 0;
-#pragma unroll
-                        for (int w = 0; w < KPL; ++w) {
-                            if (w < (int)(jpos[k] >> 5)) r += __popc(mw[w]);
-                            else if (w == (int)(jpos[k] >> 5)) r += __popc(mw[w] & ((1u << (jpos[k] & 31)) - 1u));
-                        }
-                        rank[k] = r;
-                    }
-#pragma unroll
-                    for (int w = 0; w < KPL; ++w) total += __popc(mw[w]);
-                }
-
-#pragma unroll
-                for (int k = 0; k < KPL; ++k) {
-                    if (em[k]) {
-                        const uint32_t i = gcount + rank[k];
-                        const uint32_t endv = min(e[k], lim);
-                        if (direct) {
-                            const unsigned long long gi = gbase + i;
-                            if (gi < (unsigned long long)P.out_cap) {
-                                P.scr_start[gi] = p;
-                                P.scr_end[gi] = endv;
-                                P.scr_order[gi] = jpos[k] + 1u;
-                            }
-                        } else if (i < (uint32_t)K) {
-                            stg[3 * i + 0] = p;
-                            stg[3 * i + 1] = endv;
-                            stg[3 * i + 2] = jpos[k] + 1u;
-                        }
-                    }
-                }
-                gcount += total;
-            }
-            if (direct) break;
-
-            // ---------------- the tile's block in the scratch area
-            // exclusive prefix of the group counts (group leaders carry the count)
-            const uint32_t mycnt = (glive && lg == 0) ? gcount : 0u;
-            uint32_t incl = mycnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            const uint32_t gprefix = __shfl_sync(FULL, incl - mycnt, glive ? g * GW : 0);
-            const bool ovf = __any_sync(FULL, glive && gcount > (uint32_t)K);
-            unsigned long long base = 0;
-            if (lane == 0) {
-                if (total) base = atomicAdd(P.cursor, (unsigned long long)total);
-                P.tile_cnt[tile] = total;
-                P.tile_off[tile] = base;
-            }
-            base = __shfl_sync(FULL, base, 0);
-            gbase = base + gprefix;
-            __syncwarp();
-            if (!ovf) {
-                if (glive) {
-                    for (uint32_t i = lg; i < gcount; i += GW) {
-                        const unsigned long long gi = gbase + i;
-                        if (gi < (unsigned long long)P.out_cap) {
-                            P.scr_start[gi] = stg[3 * i + 0];
-                            P.scr_end[gi] = stg[3 * i + 1];
-                            P.scr_order[gi] = stg[3 * i + 2];
-                        }
-                    }
-                }
-                break;
-            }
-            ++replays;      // staging overflowed: recompute the tile with direct stores
-        }
-        __syncwarp();                    // stage s, list and staging are free again
-        if (lane == 0) issue(s, tile + (long long)S * n_warps);
-        if (++s == S) {
-            s = 0;
-            parity ^= 1u;
-        }
-    }
-    if (irr_acc >> 31) P.result[MEMO_RES_IRREGULAR] = 1;
-    if (lane == 0 && replays) atomicAdd((unsigned long long*)(P.result + MEMO_RES_REPLAYS), replays);
-}
-
-// ---------------------------------------------------------------- kernel 2
+// ---------------------------------------------------------------- scan
 // partial[b] = index rows of tile block b; the last block to arrive turns
 // partial[] into exclusive block offsets and writes the grand total.
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -467,7 +90,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_cnt, long long n_tiles,
     if (threadIdx.x == 0) result[MEMO_RES_N_OUT] = (int64_t)carry;
 }
 
-// ---------------------------------------------------------------- kernel 3
+// ---------------------------------------------------------------- gather
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
                    long long n_tiles, const unsigned long long* __restrict__ block_base,
@@ -475,7 +98,7 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
                    const uint32_t* __restrict__ scr_start, const uint32_t* __restrict__ scr_end,
                    const uint32_t* __restrict__ scr_order, int32_t* __restrict__ out_start,
                    uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                   long long scr_cap, int64_t* __restrict__ seg_out_end) {
+                   long long scr_cap, int mult, int64_t* __restrict__ seg_out_end) {
     __shared__ uint32_t excl[SCAN_BLOCK];          // exclusive row offset of each tile in the block
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
@@ -514,7 +137,7 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
     // rows emitted up to the end of each record run that ends in this block:
     // run s ends where tile seg_tile_start[s + 1] begins
     for (int s = threadIdx.x; s < n_seg; s += SCAN_THREADS) {
-        const long long t = seg_tile_start[s + 1];
+        const long long t = seg_tile_start[s + 1] * mult;
         if (t > blk_lo && t <= blk_hi) {
             const uint32_t e = (t == blk_hi) ? block_total : excl[t - blk_lo];
             seg_out_end[s] = (int64_t)(base + e);
@@ -560,50 +183,14 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
 }
 
 // ---------------------------------------------------------------- host side
-// phase B shape: KPL columns per lane; for KPL == 1 a row group is gw lanes wide
-struct Geometry {
-    int KPL, gw, all_pairs, sl, wcols, rb;
-};
-
-bool pick_geometry(int C, Geometry* geo) {
-    static const int kpls[] = {1, 2, 3, 4, 6, 8, 16};
-    for (int kpl : kpls)
-        if (32 * kpl >= C) {
-            geo->KPL = kpl;
-            geo->gw = (kpl == 1 && C <= 16) ? C : 32;
-            geo->all_pairs = (kpl == 1 && C <= 12) ? 1 : 0;
-            geo->sl = geo->wcols = geo->rb = 0;          // phase A shape: set_scan_shape()
-            return true;
-        }
-    return false;
-}
-
-// phase A shape for tiles of T rows: sl lanes share a row block (sl a power of two),
-// 32 / sl row blocks of rb <= RBMAX rows
-void set_scan_shape(int C, int T, Geometry* geo) {
-    int sl = 1;
-    while (sl < 32 && (32 / (2 * sl)) >= T) sl *= 2;     // no more rows per step than rows
-    geo->sl = sl;
-    geo->wcols = (C + sl - 1) / sl;
-    geo->rb = 0;
-}
-
-stream_kernel_t select_kernel(const Geometry& g, bool order, int C, int ld) {
-#define MEMO_CASE(KK) \
-    if (g.KPL == KK) return order ? stream_kernel<KK, true, 0> : stream_kernel<KK, false, 0>;
-    MEMO_CASE(1) MEMO_CASE(2) MEMO_CASE(3) MEMO_CASE(4) MEMO_CASE(6) MEMO_CASE(8) MEMO_CASE(16)
-#undef MEMO_CASE
-    return nullptr;
-}
-
 struct FastPlan {
-    Geometry geo;
     int narrow, rpl;            // lane-per-row kernel (index_narrow.cu) and its rows per lane
-    int T, K, stages, warps, ctas_per_sm;
+    int kpl;                    // wide kernel: sorted positions per lane
+    int T, R, mult, stages, warps, ctas_per_sm;
     uint32_t chunk;             // scratch rows per warp reservation
     long long scr_cap;          // entries per scratch array
     uint32_t stage_bytes, warp_smem, off_bars, off_descs, off_stg, off_list;
-    long long n_tiles, n_blocks;
+    long long n_units, n_slots, n_blocks;
     size_t smem;
     size_t off_segs, off_tstart, off_cnt, off_off, off_partial, off_ctrl, off_scratch, total;
 };
@@ -614,11 +201,11 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     MEMO_REQUIRE(ld >= C, "ld must be >= n_cols");
     MEMO_REQUIRE(out_cap >= 0, "out_cap must be >= 0");
     MEMO_REQUIRE(n_seg >= 0 && (n_seg == 0 || segs != nullptr), "bad segment table");
-    if (!pick_geometry(C, &plan->geo)) {
+    plan->kpl = 0;
+    if (select_wide_kernel(C, true, &plan->kpl) == nullptr) {
         set_error("n_cols = %d not supported (max 512)", C);
         return MEMO_ERR_UNSUPPORTED;
     }
-    const int groups = 32 / plan->geo.gw;
     plan->warps = (opts && opts->warps_per_cta > 0) ? opts->warps_per_cta : 8;
     MEMO_REQUIRE(plan->warps >= 1 && plan->warps <= 8, "warps_per_cta must be 1..8");
     plan->stages = (opts && opts->stages > 0) ? opts->stages : 2;
@@ -629,48 +216,56 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->narrow = (ld == C && !(opts && opts->kernel_variant == 1) &&
                     select_narrow_kernel(C, true, &plan->rpl) != nullptr) ? 1 : 0;
     if (!plan->narrow) plan->rpl = 1;
+
+    // scratch: warps reserve it in chunks, which wastes < 1/4 of every chunk plus
+    // each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice
+    const long long max_warps = (long long)device_sm_count() * 32;
+    long long chunk = 4096;
+    while (chunk > 256 && chunk * max_warps * 8 > out_cap) chunk >>= 1;
+    while (chunk < 4ll * C) chunk <<= 1;
+    plan->chunk = (uint32_t)chunk;
+    plan->scr_cap = out_cap > 0 ? ((out_cap + max_warps * chunk) * 4 / 3 + 64) & ~3ll : 0;
+
+    // a warp's stages must fit its share of the SM's shared memory
+    const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
     long long T;
+    size_t extra = 0;
     if (plan->narrow) {
-        // whole warp steps of 32 * rpl rows, ~4.5-9 KB of DAP per tile
+        // tiles: whole warp steps of 32 * rpl rows, ~4.5-9 KB of DAP per tile
         const long long step = 32ll * plan->rpl;
         long long it = (opts && opts->rows_per_tile > 0) ? (opts->rows_per_tile + step - 1) / step
                                                           : (5632 + step * row_bytes / 2) / (step * row_bytes);
         if (it < 1) it = 1;
-        // keep the CTA's stages within the SM's shared memory
-        const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
         while (it > 1 && (it * step > MAX_TILE_ROWS || (it * step + 2) * row_bytes + 144 > budget)) --it;
         T = it * step;
-        plan->T = (int)T;
-        plan->K = 0;
+        plan->R = 0;
+        plan->mult = 1;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
+        extra = 4 * 32 * (size_t)(C | 1) + 2 * (size_t)(T + 4);       // end columns + row list
     } else {
-        // a stage holds T + 2 rows; keep a warp's stages within its share of the SM
-        const long long stage_budget = (200 * 1024 / plan->warps - 1536) / plan->stages;
-        if (opts && opts->rows_per_tile > 0) {
-            T = opts->rows_per_tile;
-        } else {
-            T = 5632 / row_bytes - 2;                // ~5.5 KB of DAP per tile: 16 warps per SM
-        }
+        // strips of R rows stream through the ring in chunks of T rows (~5.5 KB)
+        T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 5632 / row_bytes;
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
-        if ((T + 2) * row_bytes + 64 > stage_budget) T = (stage_budget - 64) / row_bytes - 2;
+        if (T * row_bytes + 160 > budget) T = (budget - 160) / row_bytes;
         if (T < 1) T = 1;
-        plan->T = (int)T;
-        set_scan_shape(C, plan->T, &plan->geo);
-        plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 64), 128);
-        if (opts && opts->emit_buf_records > 0) {
-            plan->K = opts->emit_buf_records;
-        } else {
-            long long k = (T * C) / (16ll * groups);  // ~10x the HPRC-shaped density
-            if (k < 8) k = 8;
-            if (k > 128) k = 128;
-            plan->K = (int)k;
-        }
+        // a strip writes at most (R + 1) n_cols index rows in at most `mult` blocks:
+        // a block ends when < n_cols <= chunk / 4 rows of the warp's chunk are left
+        long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : 256;
+        const long long r_max = 14 * chunk / C - 1;
+        if (R > r_max) R = r_max;
+        if (R < 1) R = 1;
+        plan->R = (int)R;
+        plan->mult = (int)(2 * (R + 1) * C / chunk + 3);
+        MEMO_REQUIRE(plan->mult <= 32, "internal: %d blocks per strip", plan->mult);
+        plan->stage_bytes = (uint32_t)align_up((size_t)(T * row_bytes + 32), 128);
     }
+    plan->T = (int)T;
     size_t o = (size_t)plan->stages * plan->stage_bytes;
     plan->off_bars = (uint32_t)o;    o += 8 * MAX_STAGES;
     plan->off_descs = (uint32_t)o;   o += sizeof(TileDesc) * MAX_STAGES;
-    plan->off_stg = (uint32_t)o;     o += plan->narrow ? 4 * 32 * (size_t)(C | 1) : 12 * (size_t)groups * plan->K;
-    plan->off_list = (uint32_t)o;    o += 2 * (size_t)(T + 4);
+    plan->off_stg = (uint32_t)o;     o += plan->narrow ? 4 * 32 * (size_t)(C | 1) : 0;
+    plan->off_list = (uint32_t)o;    o += plan->narrow ? 2 * (size_t)(T + 4) : 0;
+    (void)extra;
     plan->warp_smem = (uint32_t)align_up(o, 128);
     plan->smem = (size_t)plan->warp_smem * plan->warps;
     MEMO_REQUIRE(plan->smem <= 227 * 1024, "tile configuration needs %zu B of shared memory", plan->smem);
@@ -696,28 +291,22 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
             const long long g = ((fc - 1) / plan->rpl) * plan->rpl;
             nt = lc >= fc ? (lc - g + T - 1) / T : 0;
         } else {
-            nt = (s.n_rows - primed + T - 1) / T;
+            nt = (s.n_rows - primed + plan->R - 1) / plan->R;
         }
-        t += nt > 0 ? nt : 1;
+        t += nt > 0 ? nt : 1;          // a one-row run still owns its chr-end rows
     }
     if (tstart_host) tstart_host[n_seg] = t;
-    plan->n_tiles = t;
-    plan->n_blocks = (t + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    plan->n_units = t;
+    plan->n_slots = t * plan->mult;
+    plan->n_blocks = (plan->n_slots + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const size_t ns = (size_t)(plan->n_slots > 0 ? plan->n_slots : 1);
     size_t off = 0;
     plan->off_segs = off;    off = align_up(off + sizeof(memo_segment_t) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
     plan->off_tstart = off;  off = align_up(off + sizeof(long long) * (size_t)(n_seg + 1), 256);
-    plan->off_cnt = off;     off = align_up(off + 4 * (size_t)(t > 0 ? t : 1), 256);
-    plan->off_off = off;     off = align_up(off + 8 * (size_t)(t > 0 ? t : 1), 256);
+    plan->off_cnt = off;     off = align_up(off + 4 * ns, 256);
+    plan->off_off = off;     off = align_up(off + 8 * ns, 256);
     plan->off_partial = off; off = align_up(off + 8 * (size_t)(plan->n_blocks > 0 ? plan->n_blocks : 1), 256);
     plan->off_ctrl = off;    off = align_up(off + 256, 256);
-    // scratch: warps reserve it in chunks (warp_alloc), which wastes < 1/4 of every
-    // chunk plus each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice
-    const long long max_warps = (long long)device_sm_count() * 32;
-    long long chunk = 4096;
-    while (chunk > 256 && chunk * max_warps * 8 > out_cap) chunk >>= 1;
-    while (chunk < 4ll * C) chunk <<= 1;
-    plan->chunk = (uint32_t)chunk;
-    plan->scr_cap = out_cap > 0 ? ((out_cap + max_warps * chunk) * 4 / 3 + 64) & ~3ll : 0;
     plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
     plan->total = off;
     return MEMO_OK;
@@ -763,7 +352,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     }
     cudaError_t e0 = cudaMemsetAsync(result, 0, sizeof(int64_t) * MEMO_RES_SLOTS, stream);
     if (e0 != cudaSuccess) { delete[] tstart; set_error("memset result: %s", cudaGetErrorString(e0)); return MEMO_ERR_CUDA; }
-    if (n_seg == 0 || plan.n_tiles == 0) { delete[] tstart; return MEMO_OK; }
+    if (n_seg == 0 || plan.n_units == 0) { delete[] tstart; return MEMO_OK; }
 
     char* ws = static_cast<char*>(workspace);
     // pageable host -> device copies are staged by the runtime before returning,
@@ -785,10 +374,9 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.C = n_cols; P.ld = ld;
     P.segs = reinterpret_cast<const memo_segment_t*>(ws + plan.off_segs);
     P.seg_tile_start = reinterpret_cast<const long long*>(ws + plan.off_tstart);
-    P.n_seg = n_seg; P.n_tiles = plan.n_tiles; P.T = plan.T; P.K = plan.K;
+    P.n_seg = n_seg; P.n_tiles = plan.n_units; P.T = plan.T; P.R = plan.R; P.maxb = plan.mult;
     P.stages = plan.stages; P.stage_bytes = plan.stage_bytes; P.warp_smem = plan.warp_smem;
     P.off_bars = plan.off_bars; P.off_descs = plan.off_descs;
-    P.gw = plan.geo.gw; P.all_pairs = plan.geo.all_pairs; P.sl = plan.geo.sl; P.wcols = plan.geo.wcols; P.rb = plan.geo.rb;
     P.off_stg = plan.off_stg; P.off_list = plan.off_list;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(ws + plan.off_scratch);
     const size_t cap4 = (size_t)plan.scr_cap;
@@ -797,14 +385,15 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.tile_cnt = reinterpret_cast<uint32_t*>(ws + plan.off_cnt);
     P.tile_off = reinterpret_cast<unsigned long long*>(ws + plan.off_off);
     P.cursor = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl);
+    P.strip_counter = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl + 128);
     unsigned int* done = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 64);
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(ws + plan.off_partial);
     P.result = result;
 
     stream_kernel_t kern = plan.narrow ? select_narrow_kernel(n_cols, order, nullptr)
-                                       : select_kernel(plan.geo, order, n_cols, ld);
+                                       : select_wide_kernel(n_cols, order, nullptr);
     if (!kern) {
-        set_error("no kernel for KPL=%d", plan.geo.KPL);
+        set_error("no kernel for n_cols=%d", n_cols);
         return MEMO_ERR_UNSUPPORTED;
     }
     const int threads = plan.warps * 32;
@@ -817,18 +406,18 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     }
     if (plan.ctas_per_sm > 0 && plan.ctas_per_sm < per_sm) per_sm = plan.ctas_per_sm;
     long long grid = (long long)device_sm_count() * per_sm;
-    const long long need = (plan.n_tiles + plan.warps - 1) / plan.warps;
+    const long long need = (plan.n_units + plan.warps - 1) / plan.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, 256, stream));
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     MEMO_CUDA_TRY(cudaGetLastError());
-    tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_tiles, partial,
+    tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_slots, partial,
                                                                           done, result);
     MEMO_CUDA_TRY(cudaGetLastError());
     tile_gather_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(
-        P.tile_cnt, P.tile_off, plan.n_tiles, partial, P.seg_tile_start, n_seg, P.scr_start, P.scr_end,
-        P.scr_order, out_start, out_end, out_order, out_cap, plan.scr_cap, seg_out_end);
+        P.tile_cnt, P.tile_off, plan.n_slots, partial, P.seg_tile_start, n_seg, P.scr_start, P.scr_end,
+        P.scr_order, out_start, out_end, out_order, out_cap, plan.scr_cap, plan.mult, seg_out_end);
     MEMO_CUDA_TRY(cudaGetLastError());
     return MEMO_OK;
 }

@@ -14,13 +14,13 @@ constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gather block
 
 struct TileDesc {
-    int n;              // compare rows 1..n (row 0 of the tile is the predecessor row)
+    int n;              // rows in the stage (narrow: T compare rows after row 0)
     int off;            // word offset of row 0 inside the stage data
     uint32_t pos_h;     // record-relative position of row 0
     uint32_t rec_len;
-    int flags;          // 1 = last tile of its run, 2 = chr-end rows follow the run
-    int r_lo, r_hi;     // narrow kernel: live compare rows of the tile are r_lo..r_hi (1-based)
-    int pad;
+    int flags;          // narrow: 1 = last tile of its run, 2 = chr-end rows follow the run; wide: WD_*
+    int r_lo, r_hi;     // narrow: live compare rows of the tile are r_lo..r_hi (1-based); wide: r_lo = strip
+    int pad;            // narrow: tile row of the run's last row
 };
 
 struct FastParams {
@@ -32,15 +32,13 @@ struct FastParams {
     const long long* seg_tile_start;   // device [n_seg + 1]
     int32_t n_seg;
     long long n_tiles;
-    int32_t T;                         // compare rows per tile
-    int32_t K;                         // staged index rows per group
+    int32_t T;                         // narrow: compare rows per tile; wide: rows per chunk
+    int32_t R;                         // wide: compare rows per strip
+    int32_t maxb;                      // slots (scratch blocks) per work unit
     int32_t stages;
     uint32_t stage_bytes;
     uint32_t warp_smem;                // shared-memory bytes per warp
     uint32_t off_bars, off_descs, off_stg, off_list;   // inside the warp's region
-    int32_t gw;                        // phase B: lanes per row group (KPL == 1)
-    int32_t all_pairs;                 // phase B: all-pairs counting (narrow rows)
-    int32_t sl, wcols, rb;             // phase A: lanes per row, columns per lane, rows per lane
     uint32_t* scr_start;               // scratch index rows (unordered tile blocks)
     uint32_t* scr_end;
     uint32_t* scr_order;
@@ -50,6 +48,7 @@ struct FastParams {
     uint32_t* tile_cnt;                // [n_tiles]
     unsigned long long* tile_off;      // [n_tiles] scratch offset of the tile's block
     unsigned long long* cursor;        // scratch allocation cursor
+    unsigned long long* strip_counter; // wide: next strip to hand out
     int64_t* result;
 };
 
@@ -120,6 +119,10 @@ __device__ __forceinline__ unsigned long long warp_alloc(const FastParams& P, un
 typedef void (*stream_kernel_t)(const FastParams);
 
 }  // namespace
+
+// index_wide.cu: strip kernel for any n_cols <= 512 (nullptr beyond); *kpl = sorted
+// positions per lane.
+stream_kernel_t select_wide_kernel(int n_cols, bool order, int* kpl);
 
 // index_narrow.cu: kernel for n_cols == ld == CT (compile-time) rows, or nullptr.
 // *rows_per_lane receives the number of consecutive rows a lane scans per step
