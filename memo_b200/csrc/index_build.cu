@@ -22,13 +22,14 @@
 //      narrow_kernel  n_cols <= 16: unit = tile of T rows, one lane per row
 //      wide_kernel    otherwise:    unit = strip of R rows, one warp per strip,
 //                     sorted row kept in registers and updated incrementally
-//    Every unit owns `mult` slots of tile_cnt / tile_off describing the blocks
-//    of scratch rows it wrote.
-//  2 tile_scan_kernel   block sums of the slot counts; the last block to finish
+//    A unit's index rows are one block of consecutive scratch rows (wide: or a
+//    short chain of blocks); tile_cnt / tile_off describe it.
+//  2 tile_scan_kernel   block sums of the unit counts; the last block to finish
 //    scans the block sums.
-//  3 tile_gather_kernel exclusive scan inside each block of slots and copy of
-//    every block from the scratch area to its place in the ordered output (the
-//    extra traffic is 24 B per index row, a few % of the DAP).
+//  3 tile_gather_kernel / strip_gather_kernel   exclusive scan inside each block
+//    of units and copy of every unit's rows from the scratch area to their place
+//    in the ordered output (the extra traffic is 24 B per index row, a few % of
+//    the DAP).
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in
 // result[MEMO_RES_IRREGULAR].
@@ -91,22 +92,15 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_cnt, long long n_tiles,
 }
 
 // ---------------------------------------------------------------- gather
-__global__ void __launch_bounds__(SCAN_THREADS)
-tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
-                   long long n_tiles, const unsigned long long* __restrict__ block_base,
-                   const long long* __restrict__ seg_tile_start, int n_seg,
-                   const uint32_t* __restrict__ scr_start, const uint32_t* __restrict__ scr_end,
-                   const uint32_t* __restrict__ scr_order, int32_t* __restrict__ out_start,
-                   uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                   long long scr_cap, int mult, int64_t* __restrict__ seg_out_end) {
-    __shared__ uint32_t excl[SCAN_BLOCK];          // exclusive row offset of each tile in the block
-    __shared__ uint32_t wsum[SCAN_THREADS / 32];
-    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
-    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
-    const unsigned long long base = block_base[blockIdx.x];
+// Common first part of the gather kernels: exclusive scan of the block's unit
+// counts into excl[] (shared memory), and the per-run row totals.  Returns the
+// block's total.
+__device__ __forceinline__ uint32_t gather_block_scan(
+    const uint32_t* __restrict__ tile_cnt, long long n_tiles, long long blk_lo, long long blk_hi,
+    unsigned long long base, const long long* __restrict__ seg_tile_start, int n_seg,
+    int64_t* __restrict__ seg_out_end, bool write_segs, uint32_t* excl, uint32_t* wsum) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // exclusive scan of the block's tile counts (thread t owns SCAN_ITEMS consecutive tiles)
+    // thread t owns SCAN_ITEMS consecutive units
     uint32_t c[SCAN_ITEMS];
     uint32_t tsum = 0;
 #pragma unroll
@@ -133,16 +127,112 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
         run += c[i];
     }
     __syncthreads();
-
     // rows emitted up to the end of each record run that ends in this block:
-    // run s ends where tile seg_tile_start[s + 1] begins
-    for (int s = threadIdx.x; s < n_seg; s += SCAN_THREADS) {
-        const long long t = seg_tile_start[s + 1] * mult;
-        if (t > blk_lo && t <= blk_hi) {
-            const uint32_t e = (t == blk_hi) ? block_total : excl[t - blk_lo];
-            seg_out_end[s] = (int64_t)(base + e);
+    // run s ends where unit seg_tile_start[s + 1] begins
+    if (write_segs) {
+        for (int s = threadIdx.x; s < n_seg; s += SCAN_THREADS) {
+            const long long t = seg_tile_start[s + 1];
+            if (t > blk_lo && t <= blk_hi) {
+                const uint32_t e = (t == blk_hi) ? block_total : excl[t - blk_lo];
+                seg_out_end[s] = (int64_t)(base + e);
+            }
         }
     }
+    return block_total;
+}
+
+// Wide rows: a unit (strip) wrote one block of scratch rows, or a chain of them.
+// One warp per strip; blockIdx.y splits a block's strips over several CTAs.
+__global__ void __launch_bounds__(SCAN_THREADS)
+strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
+                    const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
+                    const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
+                    const unsigned long long* __restrict__ block_base,
+                    const long long* __restrict__ seg_tile_start, int n_seg,
+                    const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
+                    uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
+                    long long scr_cap, int64_t* __restrict__ seg_out_end) {
+    __shared__ uint32_t excl[SCAN_BLOCK];
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
+    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
+    const unsigned long long base = block_base[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start, n_seg, seg_out_end,
+                      blockIdx.y == 0, excl, wsum);
+    if (out_cap == 0) return;
+    const int n_units = (int)(blk_hi - blk_lo);
+    const int wstride = (SCAN_THREADS / 32) * gridDim.y;
+    for (int u = warp + (SCAN_THREADS / 32) * blockIdx.y; u < n_units; u += wstride) {
+        const long long g = blk_lo + u;
+        if (tile_cnt[g] == 0) continue;
+        unsigned long long dst = base + excl[u];
+        unsigned long long off = tile_off[g];
+        uint32_t cnt = first_cnt[g];
+        int32_t nx = unit_next[g];
+        for (;;) {
+            if (off + cnt <= (unsigned long long)scr_cap && dst + cnt <= (unsigned long long)out_cap) {
+                const uint32_t* src = scr + off * 3;
+                uint32_t i = lane;
+                for (; i + 96 < cnt; i += 128) {        // four rows per lane in flight
+                    uint32_t v[4][3];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t* row = src + (size_t)(i + 32 * j) * 3;
+                        v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned long long d = dst + i + 32 * j;
+                        out_start[d] = (int32_t)v[j][0];
+                        out_end[d] = v[j][1];
+                        out_order[d] = (int32_t)v[j][2];
+                    }
+                }
+                for (; i < cnt; i += 32) {
+                    const uint32_t* row = src + (size_t)i * 3;
+                    const unsigned long long d = dst + i;
+                    out_start[d] = (int32_t)row[0];
+                    out_end[d] = row[1];
+                    out_order[d] = (int32_t)row[2];
+                }
+            } else if (off + cnt <= (unsigned long long)scr_cap) {
+                for (uint32_t i = lane; i < cnt; i += 32) {
+                    const unsigned long long d = dst + i;
+                    if (d < (unsigned long long)out_cap) {
+                        const uint32_t* row = scr + (off + i) * 3;
+                        out_start[d] = (int32_t)row[0];
+                        out_end[d] = row[1];
+                        out_order[d] = (int32_t)row[2];
+                    }
+                }
+            }
+            dst += cnt;
+            if (nx < 0 || (uint32_t)nx >= pool_cap) break;
+            const BlockRec rec = pool[nx];
+            off = rec.off;
+            cnt = rec.cnt;
+            nx = rec.next;
+        }
+    }
+}
+
+// Narrow rows: every unit (tile) wrote one small block.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
+                   long long n_tiles, const unsigned long long* __restrict__ block_base,
+                   const long long* __restrict__ seg_tile_start, int n_seg,
+                   const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
+                   uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
+                   long long scr_cap, int64_t* __restrict__ seg_out_end) {
+    __shared__ uint32_t excl[SCAN_BLOCK];          // exclusive row offset of each tile in the block
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
+    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
+    const unsigned long long base = block_base[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start, n_seg, seg_out_end, true,
+                      excl, wsum);
     if (out_cap == 0) return;
 
     // copy: each warp takes batches of 32 tiles; lane <-> tile for the metadata,
@@ -173,9 +263,10 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
                 const unsigned long long src = ooff + (i - orel);
                 const unsigned long long dst = base + first + i;
                 if (src < (unsigned long long)scr_cap && dst < (unsigned long long)out_cap) {
-                    out_start[dst] = (int32_t)scr_start[src];
-                    out_end[dst] = scr_end[src];
-                    out_order[dst] = (int32_t)scr_order[src];
+                    const uint32_t* row = scr + src * 3;
+                    out_start[dst] = (int32_t)row[0];
+                    out_end[dst] = row[1];
+                    out_order[dst] = (int32_t)row[2];
                 }
             }
         }
@@ -186,13 +277,15 @@ tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long lo
 struct FastPlan {
     int narrow, rpl;            // lane-per-row kernel (index_narrow.cu) and its rows per lane
     int kpl;                    // wide kernel: sorted positions per lane
-    int T, R, mult, stages, warps, ctas_per_sm;
+    int T, R, stages, warps, ctas_per_sm;
+    uint32_t pool_cap;          // wide: BlockRec records
     uint32_t chunk;             // scratch rows per warp reservation
     long long scr_cap;          // entries per scratch array
     uint32_t stage_bytes, warp_smem, off_bars, off_descs, off_stg, off_list;
-    long long n_units, n_slots, n_blocks;
+    long long n_units, n_blocks;
     size_t smem;
-    size_t off_segs, off_tstart, off_cnt, off_off, off_partial, off_ctrl, off_scratch, total;
+    size_t off_segs, off_tstart, off_cnt, off_off, off_partial, off_ctrl, off_fcnt, off_next, off_pool,
+        off_scratch, total;
 };
 
 int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const memo_segment_t* segs,
@@ -218,13 +311,16 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     if (!plan->narrow) plan->rpl = 1;
 
     // scratch: warps reserve it in chunks, which wastes < 1/4 of every chunk plus
-    // each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice
+    // each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice.  Chunks of
+    // 2-4 K rows when the output is large enough for that slack not to matter.
     const long long max_warps = (long long)device_sm_count() * 32;
     long long chunk = 4096;
-    while (chunk > 256 && chunk * max_warps * 8 > out_cap) chunk >>= 1;
+    while (chunk > 256 && chunk * max_warps > out_cap) chunk >>= 1;
     while (chunk < 4ll * C) chunk <<= 1;
     plan->chunk = (uint32_t)chunk;
     plan->scr_cap = out_cap > 0 ? ((out_cap + max_warps * chunk) * 4 / 3 + 64) & ~3ll : 0;
+    // every chunk a strip crosses into costs one BlockRec
+    plan->pool_cap = (uint32_t)(plan->scr_cap / (chunk / 2) + max_warps + 16);
 
     // a warp's stages must fit its share of the SM's shared memory
     const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
@@ -239,25 +335,19 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         while (it > 1 && (it * step > MAX_TILE_ROWS || (it * step + 2) * row_bytes + 144 > budget)) --it;
         T = it * step;
         plan->R = 0;
-        plan->mult = 1;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
         extra = 4 * 32 * (size_t)(C | 1) + 2 * (size_t)(T + 4);       // end columns + row list
     } else {
         // strips of R rows stream through the ring in chunks of T rows (~5.5 KB)
         T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 5632 / row_bytes;
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
-        if (T * row_bytes + 160 > budget) T = (budget - 160) / row_bytes;
+        if (T * row_bytes + 160 + 128 * plan->kpl > budget) T = (budget - 160 - 128 * plan->kpl) / row_bytes;
         if (T < 1) T = 1;
-        // a strip writes at most (R + 1) n_cols index rows in at most `mult` blocks:
-        // a block ends when < n_cols <= chunk / 4 rows of the warp's chunk are left
         long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : 256;
-        const long long r_max = 14 * chunk / C - 1;
-        if (R > r_max) R = r_max;
         if (R < 1) R = 1;
         plan->R = (int)R;
-        plan->mult = (int)(2 * (R + 1) * C / chunk + 3);
-        MEMO_REQUIRE(plan->mult <= 32, "internal: %d blocks per strip", plan->mult);
-        plan->stage_bytes = (uint32_t)align_up((size_t)(T * row_bytes + 32), 128);
+        // (slots of lanes past the last column read up to 128 * kpl bytes beyond a row)
+        plan->stage_bytes = (uint32_t)align_up((size_t)(T * row_bytes + 32 + 128 * plan->kpl), 128);
     }
     plan->T = (int)T;
     size_t o = (size_t)plan->stages * plan->stage_bytes;
@@ -297,9 +387,8 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     }
     if (tstart_host) tstart_host[n_seg] = t;
     plan->n_units = t;
-    plan->n_slots = t * plan->mult;
-    plan->n_blocks = (plan->n_slots + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    const size_t ns = (size_t)(plan->n_slots > 0 ? plan->n_slots : 1);
+    plan->n_blocks = (t + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const size_t ns = (size_t)(t > 0 ? t : 1);
     size_t off = 0;
     plan->off_segs = off;    off = align_up(off + sizeof(memo_segment_t) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
     plan->off_tstart = off;  off = align_up(off + sizeof(long long) * (size_t)(n_seg + 1), 256);
@@ -307,6 +396,9 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_off = off;     off = align_up(off + 8 * ns, 256);
     plan->off_partial = off; off = align_up(off + 8 * (size_t)(plan->n_blocks > 0 ? plan->n_blocks : 1), 256);
     plan->off_ctrl = off;    off = align_up(off + 256, 256);
+    plan->off_fcnt = off;    off = align_up(off + (plan->narrow ? 0 : 4 * ns), 256);
+    plan->off_next = off;    off = align_up(off + (plan->narrow ? 0 : 4 * ns), 256);
+    plan->off_pool = off;    off = align_up(off + (plan->narrow ? 0 : sizeof(BlockRec) * (size_t)plan->pool_cap), 256);
     plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
     plan->total = off;
     return MEMO_OK;
@@ -374,18 +466,21 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.C = n_cols; P.ld = ld;
     P.segs = reinterpret_cast<const memo_segment_t*>(ws + plan.off_segs);
     P.seg_tile_start = reinterpret_cast<const long long*>(ws + plan.off_tstart);
-    P.n_seg = n_seg; P.n_tiles = plan.n_units; P.T = plan.T; P.R = plan.R; P.maxb = plan.mult;
+    P.n_seg = n_seg; P.n_tiles = plan.n_units; P.T = plan.T; P.R = plan.R;
     P.stages = plan.stages; P.stage_bytes = plan.stage_bytes; P.warp_smem = plan.warp_smem;
     P.off_bars = plan.off_bars; P.off_descs = plan.off_descs;
     P.off_stg = plan.off_stg; P.off_list = plan.off_list;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(ws + plan.off_scratch);
-    const size_t cap4 = (size_t)plan.scr_cap;
-    P.scr_start = scratch; P.scr_end = scratch + cap4; P.scr_order = scratch + 2 * cap4;
+    P.scr = reinterpret_cast<uint32_t*>(ws + plan.off_scratch);
     P.out_cap = out_cap; P.scr_cap = plan.scr_cap; P.chunk = plan.chunk;
     P.tile_cnt = reinterpret_cast<uint32_t*>(ws + plan.off_cnt);
     P.tile_off = reinterpret_cast<unsigned long long*>(ws + plan.off_off);
     P.cursor = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl);
     P.strip_counter = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl + 128);
+    P.pool_counter = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 192);
+    P.first_cnt = reinterpret_cast<uint32_t*>(ws + plan.off_fcnt);
+    P.unit_next = reinterpret_cast<int32_t*>(ws + plan.off_next);
+    P.pool = reinterpret_cast<BlockRec*>(ws + plan.off_pool);
+    P.pool_cap = plan.pool_cap;
     unsigned int* done = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 64);
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(ws + plan.off_partial);
     P.result = result;
@@ -412,12 +507,23 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, 256, stream));
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     MEMO_CUDA_TRY(cudaGetLastError());
-    tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_slots, partial,
+    tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_units, partial,
                                                                           done, result);
     MEMO_CUDA_TRY(cudaGetLastError());
-    tile_gather_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(
-        P.tile_cnt, P.tile_off, plan.n_slots, partial, P.seg_tile_start, n_seg, P.scr_start, P.scr_end,
-        P.scr_order, out_start, out_end, out_order, out_cap, plan.scr_cap, plan.mult, seg_out_end);
+    if (plan.narrow) {
+        tile_gather_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(
+            P.tile_cnt, P.tile_off, plan.n_units, partial, P.seg_tile_start, n_seg, P.scr, out_start,
+            out_end, out_order, out_cap, plan.scr_cap, seg_out_end);
+    } else {
+        // enough CTAs to fill the device: split each block's strips over several CTAs
+        long long split = (4ll * device_sm_count() + plan.n_blocks - 1) / plan.n_blocks;
+        if (split < 1) split = 1;
+        if (split > SCAN_BLOCK / (SCAN_THREADS / 32)) split = SCAN_BLOCK / (SCAN_THREADS / 32);
+        strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
+            P.tile_cnt, P.tile_off, P.first_cnt, P.unit_next, P.pool, P.pool_cap, plan.n_units, partial,
+            P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
+            seg_out_end);
+    }
     MEMO_CUDA_TRY(cudaGetLastError());
     return MEMO_OK;
 }

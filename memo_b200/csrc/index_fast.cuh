@@ -23,6 +23,12 @@ struct TileDesc {
     int pad;            // narrow: tile row of the run's last row
 };
 
+struct BlockRec {          // a block of consecutive scratch rows continuing a strip's output
+    unsigned long long off;
+    uint32_t cnt;
+    int32_t next;          // index of the next BlockRec of the strip, -1 = none
+};
+
 struct FastParams {
     const int32_t* dap;
     long long total_bytes;             // rows * ld * 4
@@ -34,19 +40,22 @@ struct FastParams {
     long long n_tiles;
     int32_t T;                         // narrow: compare rows per tile; wide: rows per chunk
     int32_t R;                         // wide: compare rows per strip
-    int32_t maxb;                      // slots (scratch blocks) per work unit
     int32_t stages;
     uint32_t stage_bytes;
     uint32_t warp_smem;                // shared-memory bytes per warp
     uint32_t off_bars, off_descs, off_stg, off_list;   // inside the warp's region
-    uint32_t* scr_start;               // scratch index rows (unordered tile blocks)
-    uint32_t* scr_end;
-    uint32_t* scr_order;
+    uint32_t* scr;                     // scratch index rows (unordered blocks): {start, end, order} x scr_cap
     long long out_cap;                 // 0 = count only
-    long long scr_cap;                 // entries per scratch array
+    long long scr_cap;                 // rows of the scratch area
     uint32_t chunk;                    // scratch rows a warp reserves per atomicAdd
-    uint32_t* tile_cnt;                // [n_tiles]
-    unsigned long long* tile_off;      // [n_tiles] scratch offset of the tile's block
+    uint32_t* tile_cnt;                // [n_tiles] index rows of the unit
+    unsigned long long* tile_off;      // [n_tiles] scratch row of the unit's (first) block
+    // wide: a strip whose output crosses scratch chunks continues in further blocks
+    uint32_t* first_cnt;               // [n_tiles] rows of the first block
+    int32_t* unit_next;                // [n_tiles] next block (index into pool) or -1
+    BlockRec* pool;                    // [pool_cap] further blocks
+    uint32_t pool_cap;
+    unsigned int* pool_counter;
     unsigned long long* cursor;        // scratch allocation cursor
     unsigned long long* strip_counter; // wide: next strip to hand out
     int64_t* result;

@@ -275,9 +275,10 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
             while (mm) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
-                P.scr_start[gi] = p;
-                P.scr_end[gi] = ecol[c];
-                P.scr_order[gi] = (uint32_t)(c + 1);
+                uint32_t* dst = P.scr + gi * 3;
+                dst[0] = p;
+                dst[1] = ecol[c];
+                dst[2] = (uint32_t)(c + 1);
                 ++gi;
             }
             running += total;
@@ -304,7 +305,9 @@ stream_kernel_t select_narrow_kernel(int n_cols, bool order, int* rows_per_lane)
         if (rows_per_lane) *rows_per_lane = 4 / gcd4(CC);                          \
         return order ? narrow_kernel<CC, true> : narrow_kernel<CC, false>;         \
     }
-    MEMO_NARROW(4) MEMO_NARROW(9)
+    MEMO_NARROW(1) MEMO_NARROW(2) MEMO_NARROW(3) MEMO_NARROW(4) MEMO_NARROW(5) MEMO_NARROW(6)
+    MEMO_NARROW(7) MEMO_NARROW(8) MEMO_NARROW(9) MEMO_NARROW(10) MEMO_NARROW(11) MEMO_NARROW(12)
+    MEMO_NARROW(13) MEMO_NARROW(14) MEMO_NARROW(15) MEMO_NARROW(16)
 #undef MEMO_NARROW
     return nullptr;
 }

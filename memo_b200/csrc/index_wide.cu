@@ -23,10 +23,10 @@
 // through the warp's private shared-memory ring in chunks of T rows (bulk async
 // copies + mbarriers, several chunks in flight), so a warp never waits for
 // another warp.  Index rows go straight to the scratch area: a warp reserves
-// P.chunk rows at a time (one atomicAdd) and appends to them; the blocks a strip
-// wrote are recorded in the strip's slots of tile_cnt / tile_off, and
-// tile_scan_kernel / tile_gather_kernel (index_build.cu) copy the blocks into
-// the ordered output.
+// P.chunk rows at a time (one atomicAdd) and appends to them, so a strip's output
+// is one block of consecutive scratch rows, or a short chain of blocks when it
+// crosses into the warp's next chunk.  tile_scan_kernel / strip_gather_kernel
+// (index_build.cu) copy the blocks into the ordered output.
 #include "index_fast.cuh"
 #include "warp_sort.cuh"
 
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
-    const int C = P.C, ld = P.ld, S = P.stages, T = P.T, R = P.R, MAXB = P.maxb;
+    const int C = P.C, ld = P.ld, S = P.stages, T = P.T, R = P.R;
 
     unsigned char* const wbase = smem_raw + (size_t)warp * P.warp_smem;
     uint64_t* const bars = (uint64_t*)(wbase + P.off_bars);
@@ -139,32 +139,66 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
         for (int s = 0; s < S; ++s) issue(s);
 
     // ---------------- consumer state
-    // raw columns: slot k of lane l is DAP column l + 32 k (clamped: lanes past the
-    // last column repeat it and are masked out of every vote)
-    int col[KPL];
-    unsigned vmask[KPL];
+    // raw columns: slot k of lane l is DAP column l + 32 k.  Slots past the last
+    // column read whatever follows the row (the stage is padded) and are masked.
+    bool cvalid[KPL];
+    uint32_t vm[KPL];
 #pragma unroll
     for (int k = 0; k < KPL; ++k) {
-        const int c = lane + 32 * k;
-        col[k] = c < C ? c : C - 1;
-        vmask[k] = __ballot_sync(FULL, c < C);
+        cvalid[k] = lane + 32 * k < C;
+        vm[k] = cvalid[k] ? 0xFFFFFFFFu : 0u;
+        asm volatile("" : "+r"(vm[k]));        // keep it a mask: one LOP3 per slot in the row loop
     }
+    const int ibase = lane * KPL;      // ORDER: first sorted position of the lane
     uint32_t prv[KPL];                 // previous row, raw values
-    uint32_t A[KPL];                   // ORDER: sorted MEM ends of the previous row, position lane*KPL + k
+    uint32_t A[KPL];                   // ORDER: sorted MEM ends of the previous row, position ibase + k
 #pragma unroll
     for (int k = 0; k < KPL; ++k) prv[k] = A[k] = 0;
     unsigned long long w_cur = 0, w_end = 0;       // the warp's reserved scratch rows
-    unsigned long long blk_off = 0, my_off = 0;    // open block; lane b keeps closed block b of the strip
-    uint32_t blk_cnt = 0, my_cnt = 0;
-    int nb = 0;
+    unsigned long long blk_off = 0;                // open block of the strip
+    uint32_t blk_cnt = 0, strip_total = 0;
+    int nblk = 0, last_rec = -1;                   // blocks closed so far; pool index of the last one
+    long long strip = 0;
     uint32_t irr_acc = 0;
 
-    // append `total` index rows (warp uniform, <= n_cols) to the strip's output;
-    // returns the scratch row of the first one
-    auto reserve = [&](uint32_t total) -> unsigned long long {
+    // close the strip's open block: the first one is described by the strip's own
+    // entries, later ones by pool records chained from it
+    auto close_block = [&]() {
+        if (nblk == 0) {
+            if (lane == 0) {
+                P.tile_off[strip] = blk_off;
+                P.first_cnt[strip] = blk_cnt;
+                P.unit_next[strip] = -1;
+            }
+        } else {
+            int idx = 0;
+            if (lane == 0) {
+                idx = (int)atomicAdd(P.pool_counter, 1u);
+                if ((uint32_t)idx < P.pool_cap) {
+                    BlockRec rec;
+                    rec.off = blk_off; rec.cnt = blk_cnt; rec.next = -1;
+                    P.pool[idx] = rec;
+                    if (nblk == 1) P.unit_next[strip] = idx; else P.pool[last_rec].next = idx;
+                }
+            }
+            last_rec = __shfl_sync(FULL, idx, 0);
+        }
+        ++nblk;
+    };
+
+    // index rows of one row: em[k] / endv[k] per slot, `p` = BED start.  Output
+    // order: ORDER -> position ibase + k; else column lane + 32 k.
+    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t p) {
+        unsigned b[KPL];
+        uint32_t total = 0, rank = 0;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            b[k] = __ballot_sync(FULL, em[k]);
+            total += __popc(b[k]);
+        }
+        if (total == 0) return;
         if (total > w_end - w_cur) {               // next chunk: the strip continues in a new block
-            if (lane == nb) { my_off = blk_off; my_cnt = blk_cnt; }
-            ++nb;
+            close_block();
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.cursor, (unsigned long long)P.chunk);
             base = __shfl_sync(FULL, base, 0);
@@ -173,42 +207,27 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
             blk_off = base;
             blk_cnt = 0;
         }
-        const unsigned long long at = w_cur;
+        if (w_cur + total <= (unsigned long long)P.scr_cap) {
+            uint32_t* const dst0 = P.scr + w_cur * 3;          // warp uniform
+            if (ORDER) {
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
+            }
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
+                if (em[k]) {
+                    uint32_t* dst = dst0 + rk * 3u;
+                    dst[0] = p;
+                    dst[1] = endv[k];
+                    dst[2] = (uint32_t)(ORDER ? ibase + k : lane + 32 * k) + 1u;
+                }
+                if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
+            }
+        }
         w_cur += total;
         blk_cnt += total;
-        return at;
-    };
-
-    // index rows of one row: em[k] / end[k] per slot, `p` = BED start
-    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t p) {
-        unsigned b[KPL];
-        uint32_t total = 0;
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) {
-            b[k] = __ballot_sync(FULL, em[k]);
-            total += __popc(b[k]);
-        }
-        if (total == 0) return;
-        const unsigned long long at = reserve(total);
-        // rank in output order: ORDER -> position lane*KPL + k; else column lane + 32 k
-        uint32_t rank = 0;
-        if (ORDER) {
-#pragma unroll
-            for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
-        }
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) {
-            const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
-            if (em[k]) {
-                const unsigned long long gi = at + rk;
-                if (gi < (unsigned long long)P.scr_cap) {
-                    P.scr_start[gi] = p;
-                    P.scr_end[gi] = endv[k];
-                    P.scr_order[gi] = (uint32_t)(ORDER ? lane * KPL + k : lane + 32 * k) + 1u;
-                }
-            }
-            if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
-        }
+        strip_total += total;
     };
 
     int s = 0;
@@ -217,31 +236,36 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
         mbar_wait(&bars[s], parity);
         const TileDesc d = descs[s];
         if (d.flags & WD_END) break;
-        const uint32_t* const sdata = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes) + d.off;
-        int r = 0;
+        // the lane's column of the stage: row r, slot k at lp[r * ld + 32 * k]
+        const uint32_t* lp = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes) + d.off + lane;
+        uint32_t pos = d.pos_h;                                  // position of the row at lp
+        int left = d.n;
         if (d.flags & WD_FIRST) {
             // strip start: row 0 only primes the state
 #pragma unroll
-            for (int k = 0; k < KPL; ++k) prv[k] = sdata[col[k]];
+            for (int k = 0; k < KPL; ++k) prv[k] = lp[32 * k];
             if (ORDER) {
 #pragma unroll
-                for (int k = 0; k < KPL; ++k) A[k] = (lane + 32 * k < C) ? prv[k] + d.pos_h : 0u;
+                for (int k = 0; k < KPL; ++k) A[k] = cvalid[k] ? prv[k] + pos : 0u;
                 group_sort_desc<32, KPL>(A, lane);
             }
-            nb = 0;
+            strip = d.r_lo;
+            nblk = 0;
             blk_off = w_cur;
             blk_cnt = 0;
-            r = 1;
+            strip_total = 0;
+            lp += ld;
+            ++pos;
+            --left;
         }
-        for (; r < d.n; ++r) {
-            const uint32_t pos = d.pos_h + (uint32_t)r;          // position of this row
-            const uint32_t* rowp = sdata + r * ld;
-            uint32_t cur[KPL], dk[KPL], acc = 0;
+        // one row: `cur` = its raw values (returned), `prev` = the row before
+        auto row = [&](const uint32_t (&prev)[KPL], uint32_t (&cur)[KPL]) {
+            uint32_t dk[KPL], acc = 0;
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
-                cur[k] = rowp[col[k]];
-                dk[k] = cur[k] + 1u - prv[k];
-                acc |= dk[k];
+                cur[k] = lp[32 * k];
+                dk[k] = cur[k] + 1u - prev[k];
+                acc |= k == KPL - 1 ? (dk[k] & vm[k]) : dk[k];
             }
             if (__any_sync(FULL, acc != 0u)) {
                 irr_acc |= acc;
@@ -251,74 +275,82 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                     uint32_t Aold[KPL];
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) Aold[k] = A[k];
+                    // cells whose MEM end moved up, one per lane and round (a decrease makes
+                    // the input irregular: flagged through irr_acc, skipped here)
+                    unsigned todo = 0;
 #pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        // cells whose MEM end moved up (a decrease makes the input irregular)
-                        unsigned m = __ballot_sync(FULL, dk[k] != 0u && !(dk[k] >> 31)) & vmask[k];
-                        while (m) {
+                    for (int k = 0; k < KPL; ++k) todo |= ((int)(dk[k] & vm[k]) > 0) ? (1u << k) : 0u;
+                    unsigned m;
+                    while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
+                        uint32_t myx = 0, myd = 0;
+#pragma unroll
+                        for (int k = KPL - 1; k >= 0; --k)
+                            if (todo & (1u << k)) { myx = prev[k]; myd = dk[k]; }
+                        todo &= todo - 1;
+                        do {
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
-                            const uint32_t x = __shfl_sync(FULL, prv[k], src) + (pos - 1u);
-                            const uint32_t y = __shfl_sync(FULL, cur[k], src) + pos;
-                            uint32_t cgt = 0, cge = 0;
-#pragma unroll
-                            for (int kk = 0; kk < KPL; ++kk) {
-                                cgt += A[kk] > y ? 1u : 0u;
-                                cge += A[kk] >= x ? 1u : 0u;
-                            }
-                            const int i_new = (int)__reduce_add_sync(FULL, cgt);
-                            const int i_old = (int)__reduce_add_sync(FULL, cge) - 1;
-                            const uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                            // delete x, insert y > x: the positions holding x <= A <= y shift
+                            // down by one and y lands on the first of them
+                            const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
+                            const uint32_t y = x + __shfl_sync(FULL, myd, src);
+                            uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                            if (lane == 0) up = 0xFFFFFFFFu;
                             uint32_t nA[KPL];
 #pragma unroll
                             for (int kk = 0; kk < KPL; ++kk) {
-                                const int i = lane * KPL + kk;
                                 const uint32_t before = kk == 0 ? up : A[kk - 1];
-                                nA[kk] = (i < i_new || i > i_old) ? A[kk] : (i == i_new ? y : before);
+                                nA[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
                             }
 #pragma unroll
                             for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
-                        }
+                        } while (m);
                     }
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) {
-                        em[k] = (lane * KPL + k < C) && A[k] > Aold[k] && Aold[k] >= pos;
+                        em[k] = A[k] > Aold[k] && Aold[k] >= pos && ibase + k < C;
                         endv[k] = Aold[k];
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) {
-                        const uint32_t e = prv[k] + (pos - 1u);
-                        em[k] = (lane + 32 * k < C) && dk[k] != 0u && !(dk[k] >> 31) && e >= pos;
+                        const uint32_t e = prev[k] + (pos - 1u);
+                        em[k] = (int)(dk[k] & vm[k]) > 0 && e >= pos;
                         endv[k] = e;
                     }
                 }
                 emit(em, endv, pos);
             }
+            lp += ld;
+            ++pos;
+        };
+        // rows alternate between two register sets (no copies); prv is the set that
+        // holds the last row seen when a chunk ends
+        uint32_t alt[KPL];
+        for (; left >= 2; left -= 2) {
+            row(prv, alt);
+            row(alt, prv);
+        }
+        if (left) {
+            row(prv, alt);
 #pragma unroll
-            for (int k = 0; k < KPL; ++k) prv[k] = cur[k];
+            for (int k = 0; k < KPL; ++k) prv[k] = alt[k];
         }
         if (d.flags & WD_LAST) {
             if (d.flags & WD_CHR) {                 // chr-end rows after the run's last row
-                const uint32_t last_pos = d.pos_h + (uint32_t)(d.n - 1);
                 bool em[KPL];
                 uint32_t endv[KPL];
 #pragma unroll
                 for (int k = 0; k < KPL; ++k) {
-                    const uint32_t e = ORDER ? A[k] : prv[k] + last_pos;
-                    const bool valid = ORDER ? (lane * KPL + k < C) : (lane + 32 * k < C);
+                    const uint32_t e = ORDER ? A[k] : prv[k] + (pos - 1u);
+                    const bool valid = ORDER ? (ibase + k < C) : cvalid[k];
                     em[k] = valid && e >= d.rec_len;
                     endv[k] = min(e, 2u * d.rec_len);
                 }
                 emit(em, endv, d.rec_len);
             }
-            // the strip's blocks -> its slots
-            if (lane == nb) { my_off = blk_off; my_cnt = blk_cnt; }
-            if (lane < MAXB) {
-                const long long slot = (long long)d.r_lo * MAXB + lane;
-                P.tile_cnt[slot] = lane <= nb ? my_cnt : 0u;
-                P.tile_off[slot] = my_off;
-            }
+            close_block();
+            if (lane == 0) P.tile_cnt[strip] = strip_total;
         }
         __syncwarp();                    // stage s is free again
         if (lane == 0) issue(s);
@@ -333,15 +365,15 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
 }  // namespace
 
 stream_kernel_t select_wide_kernel(int n_cols, bool order, int* kpl_out) {
-    static const int kpls[] = {1, 2, 3, 4, 6, 8, 16};
-    for (int kpl : kpls) {
-        if (32 * kpl < n_cols) continue;
-        if (kpl_out) *kpl_out = kpl;
+    // KPL = ceil(n_cols / 32) exactly: only a lane's last slot can lie past the last column
+    const int kpl = (n_cols + 31) / 32;
+    if (kpl_out) *kpl_out = kpl;
 #define MEMO_WIDE(KK) \
     if (kpl == KK) return order ? wide_kernel<KK, true> : wide_kernel<KK, false>;
-        MEMO_WIDE(1) MEMO_WIDE(2) MEMO_WIDE(3) MEMO_WIDE(4) MEMO_WIDE(6) MEMO_WIDE(8) MEMO_WIDE(16)
+    MEMO_WIDE(1) MEMO_WIDE(2) MEMO_WIDE(3) MEMO_WIDE(4) MEMO_WIDE(5) MEMO_WIDE(6) MEMO_WIDE(7) MEMO_WIDE(8)
+    MEMO_WIDE(9) MEMO_WIDE(10) MEMO_WIDE(11) MEMO_WIDE(12) MEMO_WIDE(13) MEMO_WIDE(14) MEMO_WIDE(15)
+    MEMO_WIDE(16)
 #undef MEMO_WIDE
-    }
     return nullptr;
 }
 

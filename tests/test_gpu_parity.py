@@ -154,7 +154,7 @@ def test_index_multi_record_and_partial(order):
     assert not res.general
 
 
-@pytest.mark.parametrize("C", [4, 9])
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 6, 7, 8, 9, 12, 15, 16])
 @pytest.mark.parametrize("order", [True, False])
 def test_index_narrow_kernel_shapes(C, order):
     """Lane-per-row kernel (index_narrow.cu): aligned tile bases vs arbitrary run
@@ -172,7 +172,7 @@ def test_index_narrow_kernel_shapes(C, order):
         assert not res.general
 
 
-@pytest.mark.parametrize("C", [4, 9])
+@pytest.mark.parametrize("C", [4, 9, 10, 40, 93])
 @pytest.mark.parametrize("shift", [1, 2, 3, 4, 7])
 def test_index_narrow_kernel_position_shards(C, shift):
     """A position shard: the buffer starts `shift` rows before the owned rows (row
