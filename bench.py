@@ -37,6 +37,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(cols):
+    """dram bytes (read + write) of one index build of the default workload, from the
+    committed `ncu --set full` capture of this kernel sequence (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(f"index_build_c{cols}")
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU during the timed region."""
 
@@ -371,15 +381,17 @@ def main():
             "query_bp_per_s": Lr * world / (qry_ms * 1e-3),
             "index_ms": idx_ms, "query_ms": qry_ms,
             "index_rows": n_owned_total, "rho_cell": n_owned_total / (Lr * world * C),
-            "replayed_strips": replays,
-            "roofline": {"kernel": "index_kernel (DAP -> index rows)", "bound": "hbm",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "memo_index_build = narrow_kernel|wide_kernel + tile_scan + gather "
+                                   "(DAP -> ordered index rows); time = CUDA events around the call",
+                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": ncu_traffic(C), "peak_source": peak_src,
                          "algorithmic_bytes": bytes_idx},
             "roofline_query": {"kernel": "query_bounds + query_conservation", "bound": "hbm",
                                "achieved": ach_q, "peak": peak, "unit": "GB/s", "frac": ach_q / peak,
                                "algorithmic_bytes": bytes_q},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e,
+            # per step: index build = stream kernel + tile_scan + gather, query = bounds + paint
+            "gpu_launches": 5 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -299,16 +299,17 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         set_error("n_cols = %d not supported (max 512)", C);
         return MEMO_ERR_UNSUPPORTED;
     }
-    plan->warps = (opts && opts->warps_per_cta > 0) ? opts->warps_per_cta : 8;
+    plan->rpl = 1;
+    plan->narrow = (ld == C && !(opts && opts->kernel_variant == 1) &&
+                    select_narrow_kernel(C, true, &plan->rpl) != nullptr) ? 1 : 0;
+    if (!plan->narrow) plan->rpl = 1;
+    // measured on B200: 2 x 8 warps per SM for tiles, 4 x 6 warps for strips
+    plan->warps = (opts && opts->warps_per_cta > 0) ? opts->warps_per_cta : (plan->narrow ? 8 : 6);
     MEMO_REQUIRE(plan->warps >= 1 && plan->warps <= 8, "warps_per_cta must be 1..8");
     plan->stages = (opts && opts->stages > 0) ? opts->stages : 2;
     MEMO_REQUIRE(plan->stages <= MAX_STAGES, "stages must be <= %d", MAX_STAGES);
     plan->ctas_per_sm = (opts && opts->ctas_per_sm > 0) ? opts->ctas_per_sm : 0;
     const long long row_bytes = (long long)ld * 4;
-    plan->rpl = 1;
-    plan->narrow = (ld == C && !(opts && opts->kernel_variant == 1) &&
-                    select_narrow_kernel(C, true, &plan->rpl) != nullptr) ? 1 : 0;
-    if (!plan->narrow) plan->rpl = 1;
 
     // scratch: warps reserve it in chunks, which wastes < 1/4 of every chunk plus
     // each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice.  Chunks of
@@ -338,12 +339,12 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
         extra = 4 * 32 * (size_t)(C | 1) + 2 * (size_t)(T + 4);       // end columns + row list
     } else {
-        // strips of R rows stream through the ring in chunks of T rows (~5.5 KB)
-        T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 5632 / row_bytes;
+        // strips of R rows stream through the ring in chunks of T rows (~3.75 KB)
+        T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 3840 / row_bytes;
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
         if (T * row_bytes + 160 + 128 * plan->kpl > budget) T = (budget - 160 - 128 * plan->kpl) / row_bytes;
         if (T < 1) T = 1;
-        long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : 256;
+        long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : 128;
         if (R < 1) R = 1;
         plan->R = (int)R;
         // (slots of lanes past the last column read up to 128 * kpl bytes beyond a row)
