@@ -37,14 +37,21 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cols):
-    """dram bytes (read + write) of one index build of the default workload, from the
-    committed `ncu --set full` capture of this kernel sequence (profiles/), or None."""
+def ncu_traffic(cols, whole=False):
+    """dram bytes (read + write) per launch of the streaming kernel (or of the whole
+    index build) of the default workload, from the committed `ncu --set full` capture
+    (profiles/traffic.json, scripts/ncu_traffic.py), or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(f"index_build_c{cols}")
+        data = json.load(open(path))
+        if whole:
+            return data.get(f"index_build_c{cols}")
+        for k in data.get(f"index_build_c{cols}_kernels", []):
+            if "narrow_kernel" in k["kernel"] or "wide_kernel" in k["kernel"]:
+                return k["dram_bytes"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -276,11 +283,18 @@ def main():
     barrier()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
+    lib = _lib.load()
+    lib.memo_profile_enable(1)          # CUDA events around the streaming kernel of every build
     t_begin.record()
     for i in range(args.steps):
         n_out, replays = step(evs[i])
     t_end.record()
     barrier()
+    lib.memo_profile_enable(0)
+    import ctypes
+    k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)
+    _lib.check(lib.memo_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)), "memo_profile_collect")
+    kern_ms = k_ms.value / max(k_n.value, 1)
     clocks = sampler.stop()
     total_ms = t_begin.elapsed_time(t_end)
     idx_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
@@ -292,13 +306,13 @@ def main():
     assert torch.equal(q_out, want), "query result violates conservation == 1 + #{MS >= k}"
     del want
 
-    stats = torch.tensor([total_ms, idx_ms, qry_ms, float(n_owned)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, idx_ms, qry_ms, float(n_owned), kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, idx_ms, qry_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        total_ms, idx_ms, qry_ms, kern_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[4].item()
         n_owned_total = int(sm[3].item())
     else:
         n_owned_total = n_owned
@@ -340,7 +354,7 @@ def main():
                "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,
                "steps": args.e2e_steps,
                "ms_per_step": 1e3 * t.item() / args.e2e_steps,
-               "note": "host.build_index + host.query: pinned host DAP streamed to the device in 64 MB "
+               "note": "host.build_index + host.query: pinned host DAP streamed to the device in 256 MB "
                        "chunks overlapped with the build, index rows (12 B each) and the query result "
                        "(1 B per bp) copied back to host; wall clock"}
         del host_dap
@@ -365,8 +379,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        # algorithmic bytes of one build: DAP read once + index rows written once
         bytes_idx = 4.0 * Lr * C + 12.0 * n_all
-        ach = bytes_idx / (idx_ms * 1e-3) / 1e9
+        ach = bytes_idx / (kern_ms * 1e-3) / 1e9          # dominant kernel: the streaming kernel
+        ach_build = bytes_idx / (idx_ms * 1e-3) / 1e9     # whole memo_index_build (stream + scan + gather)
         n_q_rows = n_all
         bytes_q = 12.0 * n_q_rows + 1.0 * Lr
         ach_q = bytes_q / (qry_ms * 1e-3) / 1e9
@@ -381,11 +397,16 @@ def main():
             "query_bp_per_s": Lr * world / (qry_ms * 1e-3),
             "index_ms": idx_ms, "query_ms": qry_ms,
             "index_rows": n_owned_total, "rho_cell": n_owned_total / (Lr * world * C),
-            "roofline": {"kernel": "memo_index_build = narrow_kernel|wide_kernel + tile_scan + gather "
-                                   "(DAP -> ordered index rows); time = CUDA events around the call",
+            "roofline": {"kernel": ("narrow_kernel" if C <= 16 else "wide_kernel") +
+                                   " (streaming kernel of memo_index_build: DAP -> index rows; CUDA events "
+                                   "around the launch, averaged over the timed steps)",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": ncu_traffic(C), "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_idx},
+                         "algorithmic_bytes": bytes_idx, "kernel_ms": kern_ms},
+            "roofline_index_build": {"kernel": "memo_index_build = streaming kernel + tile_scan + strip_gather",
+                                     "bound": "hbm", "achieved": ach_build, "peak": peak, "unit": "GB/s",
+                                     "frac": ach_build / peak, "algorithmic_bytes": bytes_idx,
+                                     "traffic": ncu_traffic(C, whole=True)},
             "roofline_query": {"kernel": "query_bounds + query_conservation", "bound": "hbm",
                                "achieved": ach_q, "peak": peak, "unit": "GB/s", "frac": ach_q / peak,
                                "algorithmic_bytes": bytes_q},

@@ -117,6 +117,13 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
                      int64_t out_cap, int64_t* seg_out_end, int64_t* result,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement aid: while enabled, every memo_index_build on this host thread
+ * brackets its streaming kernel (the launch that reads the DAP) with CUDA events
+ * on the build's stream.  memo_profile_collect synchronises those events, returns
+ * the summed kernel time and the number of builds, and clears them. */
+int memo_profile_enable(int32_t on);
+int memo_profile_collect(double* stream_kernel_ms, int32_t* n_builds);
+
 /* Same contract, exact for arbitrary non-negative integer input (three passes:
  * per-strip column aggregates, carry scan, emit). shard_carry_in (device
  * uint32[n_cols] or NULL) is the end of the last flagged MEM per column handed

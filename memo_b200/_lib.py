@@ -43,6 +43,8 @@ SIGNATURES = {
     "memo_index_build_general": (C.c_int, [_vp, _i64, _i32, _i32, C.POINTER(Segment), _i32,
                                            C.POINTER(IndexOpts), _vp, _vp, _vp, _vp, _vp, _i64,
                                            _vp, _vp, _vp, _sz, _vp]),
+    "memo_profile_enable": (C.c_int, [_i32]),
+    "memo_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "memo_query_workspace_bytes": (_sz, [_i64]),
     "memo_query_conservation": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32,
                                           _vp, _vp, _sz, _vp]),

@@ -19,24 +19,33 @@
 //  1 a streaming kernel reads the DAP exactly once (bulk async copies into
 //    per-warp shared-memory rings; warps never wait for each other) and appends
 //    the index rows of its work units to a scratch area, unordered:
-//      narrow_kernel  n_cols <= 16: unit = tile of T rows, one lane per row
+//      narrow_kernel  n_cols <= 16: unit = strip of G tiles of T rows, one lane per row
 //      wide_kernel    otherwise:    unit = strip of R rows, one warp per strip,
 //                     sorted row kept in registers and updated incrementally
 //    A unit's index rows are one block of consecutive scratch rows (wide: or a
 //    short chain of blocks); tile_cnt / tile_off describe it.
 //  2 tile_scan_kernel   block sums of the unit counts; the last block to finish
 //    scans the block sums.
-//  3 tile_gather_kernel / strip_gather_kernel   exclusive scan inside each block
+//  3 strip_gather_kernel   exclusive scan inside each block
 //    of units and copy of every unit's rows from the scratch area to their place
 //    in the ordered output (the extra traffic is 24 B per index row, a few % of
 //    the DAP).
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in
 // result[MEMO_RES_IRREGULAR].
+#include <vector>
+
 #include "index_fast.cuh"
 
 namespace memo {
 namespace {
+
+// event pairs around the streaming kernel (memo_profile_enable / _collect)
+struct Profile {
+    bool on = false;
+    std::vector<cudaEvent_t> events;
+};
+thread_local Profile g_profile;
 
 // ---------------------------------------------------------------- scan
 // partial[b] = index rows of tile block b; the last block to arrive turns
@@ -141,8 +150,12 @@ __device__ __forceinline__ uint32_t gather_block_scan(
     return block_total;
 }
 
-// Wide rows: a unit (strip) wrote one block of scratch rows, or a chain of them.
-// One warp per strip; blockIdx.y splits a block's strips over several CTAs.
+// A unit (strip) wrote one block of scratch rows, or a chain of them.  A CTA
+// stages the metadata of its block of 1024 units in shared memory, and its
+// threads then copy output rows independently (consecutive threads, consecutive
+// output rows): owner unit by binary search in the block's exclusive scan,
+// source row from the unit's block chain.  gridDim.y CTAs share a block of units,
+// each copying a contiguous slice of the block's rows.
 __global__ void __launch_bounds__(SCAN_THREADS)
 strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
                     const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
@@ -154,120 +167,72 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
                     long long scr_cap, int64_t* __restrict__ seg_out_end) {
     __shared__ uint32_t excl[SCAN_BLOCK];
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    __shared__ uint32_t s_fcnt[SCAN_BLOCK];
+    __shared__ int32_t s_next[SCAN_BLOCK];
+    __shared__ unsigned long long s_off[SCAN_BLOCK];
     const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
     const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
     const unsigned long long base = block_base[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start, n_seg, seg_out_end,
-                      blockIdx.y == 0, excl, wsum);
-    if (out_cap == 0) return;
+    const uint32_t block_total = gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start,
+                                                   n_seg, seg_out_end, blockIdx.y == 0, excl, wsum);
+    if (out_cap == 0 || block_total == 0) return;
     const int n_units = (int)(blk_hi - blk_lo);
-    const int wstride = (SCAN_THREADS / 32) * gridDim.y;
-    for (int u = warp + (SCAN_THREADS / 32) * blockIdx.y; u < n_units; u += wstride) {
-        const long long g = blk_lo + u;
-        if (tile_cnt[g] == 0) continue;
-        unsigned long long dst = base + excl[u];
-        unsigned long long off = tile_off[g];
-        uint32_t cnt = first_cnt[g];
-        int32_t nx = unit_next[g];
-        for (;;) {
-            if (off + cnt <= (unsigned long long)scr_cap && dst + cnt <= (unsigned long long)out_cap) {
-                const uint32_t* src = scr + off * 3;
-                uint32_t i = lane;
-                for (; i + 96 < cnt; i += 128) {        // four rows per lane in flight
-                    uint32_t v[4][3];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t* row = src + (size_t)(i + 32 * j) * 3;
-                        v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned long long d = dst + i + 32 * j;
-                        out_start[d] = (int32_t)v[j][0];
-                        out_end[d] = v[j][1];
-                        out_order[d] = (int32_t)v[j][2];
-                    }
-                }
-                for (; i < cnt; i += 32) {
-                    const uint32_t* row = src + (size_t)i * 3;
-                    const unsigned long long d = dst + i;
-                    out_start[d] = (int32_t)row[0];
-                    out_end[d] = row[1];
-                    out_order[d] = (int32_t)row[2];
-                }
-            } else if (off + cnt <= (unsigned long long)scr_cap) {
-                for (uint32_t i = lane; i < cnt; i += 32) {
-                    const unsigned long long d = dst + i;
-                    if (d < (unsigned long long)out_cap) {
-                        const uint32_t* row = scr + (off + i) * 3;
-                        out_start[d] = (int32_t)row[0];
-                        out_end[d] = row[1];
-                        out_order[d] = (int32_t)row[2];
-                    }
-                }
-            }
-            dst += cnt;
-            if (nx < 0 || (uint32_t)nx >= pool_cap) break;
+    for (int u = threadIdx.x; u < n_units; u += SCAN_THREADS) {
+        s_off[u] = tile_off[blk_lo + u];
+        s_fcnt[u] = first_cnt[blk_lo + u];
+        s_next[u] = unit_next[blk_lo + u];
+    }
+    __syncthreads();
+    // this CTA's slice of the block's rows
+    const uint32_t lo = (uint32_t)((unsigned long long)block_total * blockIdx.y / gridDim.y);
+    const uint32_t hi = (uint32_t)((unsigned long long)block_total * (blockIdx.y + 1) / gridDim.y);
+
+    // scratch row of the block's output row d (0xFF..F = not stored)
+    auto source = [&](uint32_t d) -> unsigned long long {
+        int a = 0, b = n_units - 1;                 // last unit with excl[u] <= d
+        while (a < b) {
+            const int m = (a + b + 1) >> 1;
+            if (excl[m] <= d) a = m; else b = m - 1;
+        }
+        uint32_t r = d - excl[a];
+        unsigned long long off = s_off[a];
+        uint32_t cnt = s_fcnt[a];
+        int32_t nx = s_next[a];
+        while (r >= cnt) {                          // continue in the unit's next block
+            if (nx < 0 || (uint32_t)nx >= pool_cap) return ~0ull;
+            r -= cnt;
             const BlockRec rec = pool[nx];
             off = rec.off;
             cnt = rec.cnt;
             nx = rec.next;
         }
-    }
-}
+        const unsigned long long src = off + r;
+        return src < (unsigned long long)scr_cap ? src : ~0ull;
+    };
 
-// Narrow rows: every unit (tile) wrote one small block.
-__global__ void __launch_bounds__(SCAN_THREADS)
-tile_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
-                   long long n_tiles, const unsigned long long* __restrict__ block_base,
-                   const long long* __restrict__ seg_tile_start, int n_seg,
-                   const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
-                   uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                   long long scr_cap, int64_t* __restrict__ seg_out_end) {
-    __shared__ uint32_t excl[SCAN_BLOCK];          // exclusive row offset of each tile in the block
-    __shared__ uint32_t wsum[SCAN_THREADS / 32];
-    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
-    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
-    const unsigned long long base = block_base[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start, n_seg, seg_out_end, true,
-                      excl, wsum);
-    if (out_cap == 0) return;
-
-    // copy: each warp takes batches of 32 tiles; lane <-> tile for the metadata,
-    // then the batch's rows are copied with consecutive lanes on consecutive rows
-    const int n_batches = (int)((blk_hi - blk_lo + 31) / 32);
-    for (int bt = warp; bt < n_batches; bt += SCAN_THREADS / 32) {
-        const int ti = bt * 32 + lane;
-        const bool have = blk_lo + ti < blk_hi;
-        const uint32_t my_excl = have ? excl[ti] : 0xFFFFFFFFu;
-        const uint32_t my_cnt = have ? tile_cnt[blk_lo + ti] : 0u;
-        const unsigned long long my_off = have ? tile_off[blk_lo + ti] : 0ull;
-        const uint32_t first = __shfl_sync(FULL, my_excl, 0);
-        uint32_t tot = my_cnt;
+    constexpr int U = 4;                            // rows per thread in flight
+    for (uint32_t d0 = lo + threadIdx.x; d0 < hi; d0 += U * SCAN_THREADS) {
+        unsigned long long src[U];
+        uint32_t v[U][3];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-        const uint32_t rel = have ? my_excl - first : 0xFFFFFFFFu;    // row offset of my tile in the batch
-        for (uint32_t i = lane; i < ((tot + 31u) & ~31u); i += 32) {
-            // owner tile of batch row i: the last lane whose rel <= i (rel is non-decreasing)
-            int lo = 0;
+        for (int j = 0; j < U; ++j) {
+            const uint32_t d = d0 + j * SCAN_THREADS;
+            src[j] = d < hi ? source(d) : ~0ull;
+        }
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t r = __shfl_sync(FULL, rel, lo + step);
-                if (r <= i) lo += step;
+        for (int j = 0; j < U; ++j) {
+            if (src[j] != ~0ull) {
+                const uint32_t* row = scr + src[j] * 3;
+                v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
             }
-            const uint32_t orel = __shfl_sync(FULL, rel, lo);
-            const unsigned long long ooff = __shfl_sync(FULL, my_off, lo);
-            if (i < tot) {
-                const unsigned long long src = ooff + (i - orel);
-                const unsigned long long dst = base + first + i;
-                if (src < (unsigned long long)scr_cap && dst < (unsigned long long)out_cap) {
-                    const uint32_t* row = scr + src * 3;
-                    out_start[dst] = (int32_t)row[0];
-                    out_end[dst] = row[1];
-                    out_order[dst] = (int32_t)row[2];
-                }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const unsigned long long d = base + d0 + j * SCAN_THREADS;
+            if (src[j] != ~0ull && d < (unsigned long long)out_cap) {
+                out_start[d] = (int32_t)v[j][0];
+                out_end[d] = v[j][1];
+                out_order[d] = (int32_t)v[j][2];
             }
         }
     }
@@ -311,15 +276,16 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->ctas_per_sm = (opts && opts->ctas_per_sm > 0) ? opts->ctas_per_sm : 0;
     const long long row_bytes = (long long)ld * 4;
 
-    // scratch: warps reserve it in chunks, which wastes < 1/4 of every chunk plus
-    // each warp's last one: (4/3) (out_cap + warps * chunk) rows suffice.  Chunks of
-    // 2-4 K rows when the output is large enough for that slack not to matter.
+    // scratch: warps reserve it in chunks; a request that does not fit abandons fewer
+    // rows than it asks for, and every warp leaves its last chunk unfinished:
+    // 2 out_cap + warps * chunk rows suffice.  Chunks of 1-4 K rows when the output
+    // is large enough for that slack not to matter.
     const long long max_warps = (long long)device_sm_count() * 32;
     long long chunk = 4096;
     while (chunk > 256 && chunk * max_warps > out_cap) chunk >>= 1;
     while (chunk < 4ll * C) chunk <<= 1;
     plan->chunk = (uint32_t)chunk;
-    plan->scr_cap = out_cap > 0 ? ((out_cap + max_warps * chunk) * 4 / 3 + 64) & ~3ll : 0;
+    plan->scr_cap = out_cap > 0 ? (2 * out_cap + max_warps * chunk + 64) & ~3ll : 0;
     // every chunk a strip crosses into costs one BlockRec
     plan->pool_cap = (uint32_t)(plan->scr_cap / (chunk / 2) + max_warps + 16);
 
@@ -335,7 +301,10 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         if (it < 1) it = 1;
         while (it > 1 && (it * step > MAX_TILE_ROWS || (it * step + 2) * row_bytes + 144 > budget)) --it;
         T = it * step;
-        plan->R = 0;
+        // strips of R tiles (~1 K rows): one scratch block chain and one gather unit each
+        long long G = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : (1024 + T - 1) / T;
+        if (G < 1) G = 1;
+        plan->R = (int)G;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
         extra = 4 * 32 * (size_t)(C | 1) + 2 * (size_t)(T + 4);       // end columns + row list
     } else {
@@ -381,6 +350,8 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
             const long long fc = s.row_begin + primed, lc = s.row_begin + s.n_rows - 1;
             const long long g = ((fc - 1) / plan->rpl) * plan->rpl;
             nt = lc >= fc ? (lc - g + T - 1) / T : 0;
+            if (nt < 1) nt = 1;
+            nt = (nt + plan->R - 1) / plan->R;
         } else {
             nt = (s.n_rows - primed + plan->R - 1) / plan->R;
         }
@@ -397,9 +368,9 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_off = off;     off = align_up(off + 8 * ns, 256);
     plan->off_partial = off; off = align_up(off + 8 * (size_t)(plan->n_blocks > 0 ? plan->n_blocks : 1), 256);
     plan->off_ctrl = off;    off = align_up(off + 256, 256);
-    plan->off_fcnt = off;    off = align_up(off + (plan->narrow ? 0 : 4 * ns), 256);
-    plan->off_next = off;    off = align_up(off + (plan->narrow ? 0 : 4 * ns), 256);
-    plan->off_pool = off;    off = align_up(off + (plan->narrow ? 0 : sizeof(BlockRec) * (size_t)plan->pool_cap), 256);
+    plan->off_fcnt = off;    off = align_up(off + 4 * ns, 256);
+    plan->off_next = off;    off = align_up(off + 4 * ns, 256);
+    plan->off_pool = off;    off = align_up(off + sizeof(BlockRec) * (size_t)plan->pool_cap, 256);
     plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
     plan->total = off;
     return MEMO_OK;
@@ -409,6 +380,29 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
 }  // namespace memo
 
 extern "C" {
+
+int memo_profile_enable(int32_t on) {
+    memo::g_profile.on = on != 0;
+    return MEMO_OK;
+}
+
+int memo_profile_collect(double* stream_kernel_ms, int32_t* n_builds) {
+    using namespace memo;
+    double total = 0.0;
+    const size_t n = g_profile.events.size() / 2;
+    for (size_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        MEMO_CUDA_TRY(cudaEventSynchronize(g_profile.events[2 * i + 1]));
+        MEMO_CUDA_TRY(cudaEventElapsedTime(&ms, g_profile.events[2 * i], g_profile.events[2 * i + 1]));
+        total += ms;
+        cudaEventDestroy(g_profile.events[2 * i]);
+        cudaEventDestroy(g_profile.events[2 * i + 1]);
+    }
+    g_profile.events.clear();
+    if (stream_kernel_ms) *stream_kernel_ms = total;
+    if (n_builds) *n_builds = (int32_t)n;
+    return MEMO_OK;
+}
 
 size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int64_t out_cap,
                                   const memo_segment_t* segs, int32_t n_seg,
@@ -506,20 +500,27 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, 256, stream));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_profile.on) {
+        MEMO_CUDA_TRY(cudaEventCreate(&ev0));
+        MEMO_CUDA_TRY(cudaEventCreate(&ev1));
+        MEMO_CUDA_TRY(cudaEventRecord(ev0, stream));
+    }
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     MEMO_CUDA_TRY(cudaGetLastError());
+    if (ev0) {
+        MEMO_CUDA_TRY(cudaEventRecord(ev1, stream));
+        g_profile.events.push_back(ev0);
+        g_profile.events.push_back(ev1);
+    }
     tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_units, partial,
                                                                           done, result);
     MEMO_CUDA_TRY(cudaGetLastError());
-    if (plan.narrow) {
-        tile_gather_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(
-            P.tile_cnt, P.tile_off, plan.n_units, partial, P.seg_tile_start, n_seg, P.scr, out_start,
-            out_end, out_order, out_cap, plan.scr_cap, seg_out_end);
-    } else {
-        // enough CTAs to fill the device: split each block's strips over several CTAs
-        long long split = (4ll * device_sm_count() + plan.n_blocks - 1) / plan.n_blocks;
+    {
+        // ~8 CTAs per SM in total: every block of units is copied by `split` CTAs
+        long long split = (8ll * device_sm_count() + plan.n_blocks - 1) / plan.n_blocks;
         if (split < 1) split = 1;
-        if (split > SCAN_BLOCK / (SCAN_THREADS / 32)) split = SCAN_BLOCK / (SCAN_THREADS / 32);
+        if (split > 32) split = 32;
         strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
             P.tile_cnt, P.tile_off, P.first_cnt, P.unit_next, P.pool, P.pool_cap, plan.n_units, partial,
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,

@@ -15,13 +15,20 @@ constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gath
 
 struct TileDesc {
     int n;              // rows in the stage (narrow: T compare rows after row 0)
-    int off;            // word offset of row 0 inside the stage data
+    int off;            // wide: word offset of row 0 inside the stage data; narrow: strip
     uint32_t pos_h;     // record-relative position of row 0
     uint32_t rec_len;
-    int flags;          // narrow: 1 = last tile of its run, 2 = chr-end rows follow the run; wide: WD_*
+    int flags;          // WD_* (index_fast.cuh)
     int r_lo, r_hi;     // narrow: live compare rows of the tile are r_lo..r_hi (1-based); wide: r_lo = strip
     int pad;            // narrow: tile row of the run's last row
 };
+
+// stage descriptor flags
+constexpr int WD_FIRST = 1;    // first stage of a strip (wide: row 0 is the strip's predecessor row)
+constexpr int WD_LAST = 2;     // last stage of the strip
+constexpr int WD_CHR = 4;      // chr-end rows follow (wide: the strip; narrow: the run, see WD_RUNLAST)
+constexpr int WD_END = 8;      // no more strips
+constexpr int WD_RUNLAST = 16; // narrow: last tile of its run
 
 struct BlockRec {          // a block of consecutive scratch rows continuing a strip's output
     unsigned long long off;
@@ -37,9 +44,9 @@ struct FastParams {
     const memo_segment_t* segs;        // device copy
     const long long* seg_tile_start;   // device [n_seg + 1]
     int32_t n_seg;
-    long long n_tiles;
+    long long n_tiles;                 // work units (strips)
     int32_t T;                         // narrow: compare rows per tile; wide: rows per chunk
-    int32_t R;                         // wide: compare rows per strip
+    int32_t R;                         // wide: compare rows per strip; narrow: tiles per strip
     int32_t stages;
     uint32_t stage_bytes;
     uint32_t warp_smem;                // shared-memory bytes per warp
@@ -99,31 +106,76 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 
-// Scratch allocation.  A warp reserves P.chunk rows of the scratch area with one
-// atomicAdd and hands them out locally ([w_cur, w_end), warp uniform), so that the
-// single allocation cursor sees one atomic per few hundred tiles instead of one
-// per tile.  A request that does not fit the rest of the chunk takes a fresh
-// chunk (the rest is abandoned: < chunk/4 rows) or, when it is large itself, an
-// exactly sized reservation.  Returns the first row of a contiguous block of
-// `total` rows; warp uniform.
-__device__ __forceinline__ unsigned long long warp_alloc(const FastParams& P, unsigned long long& w_cur,
-                                                         unsigned long long& w_end, uint32_t total,
-                                                         int lane) {
-    if (total <= w_end - w_cur) {
-        const unsigned long long base = w_cur;
-        w_cur += total;
-        return base;
+// Output of one work unit (strip) of a warp.  A warp reserves P.chunk rows of the
+// scratch area with one atomicAdd and appends the index rows of its strips to
+// them, so that the single allocation cursor sees one atomic per few thousand
+// index rows.  A strip's output is therefore one block of consecutive scratch
+// rows, or -- when it does not fit the rest of the warp's chunk -- a chain of
+// blocks: the first one is described by the strip's own tile_off / first_cnt /
+// unit_next entries, later ones by BlockRec pool records.  A request that does
+// not fit abandons the rest of the chunk (fewer rows than the request itself, so
+// at most half of the reserved rows are ever wasted).  All members are warp
+// uniform; every method must be called by the whole warp.
+struct StripOut {
+    unsigned long long w_cur = 0, w_end = 0;       // the warp's reserved scratch rows
+    unsigned long long blk_off = 0;                // open block of the strip
+    uint32_t blk_cnt = 0, total = 0;               // rows in the open block / in the strip
+    int nblk = 0, last_rec = -1;                   // blocks closed so far; pool index of the last one
+    long long strip = 0;
+
+    __device__ __forceinline__ void begin(long long strip_id) {
+        strip = strip_id;
+        nblk = 0;
+        blk_off = w_cur;
+        blk_cnt = 0;
+        total = 0;
     }
-    const bool big = total > P.chunk / 4;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.cursor, (unsigned long long)(big ? total : P.chunk));
-    base = __shfl_sync(FULL, base, 0);
-    if (!big) {
-        w_cur = base + total;
-        w_end = base + P.chunk;
+    __device__ __forceinline__ void close_block(const FastParams& P, int lane) {
+        if (nblk == 0) {
+            if (lane == 0) {
+                P.tile_off[strip] = blk_off;
+                P.first_cnt[strip] = blk_cnt;
+                P.unit_next[strip] = -1;
+            }
+        } else {
+            int idx = 0;
+            if (lane == 0) {
+                idx = (int)atomicAdd(P.pool_counter, 1u);
+                if ((uint32_t)idx < P.pool_cap) {
+                    BlockRec rec;
+                    rec.off = blk_off; rec.cnt = blk_cnt; rec.next = -1;
+                    P.pool[idx] = rec;
+                    if (nblk == 1) P.unit_next[strip] = idx; else P.pool[last_rec].next = idx;
+                }
+            }
+            last_rec = __shfl_sync(FULL, idx, 0);
+        }
+        ++nblk;
     }
-    return base;
-}
+    // `n` consecutive scratch rows for the strip's next index rows; returns the first
+    __device__ __forceinline__ unsigned long long reserve(const FastParams& P, uint32_t n, int lane) {
+        if (n > w_end - w_cur) {                   // next chunk: the strip continues in a new block
+            close_block(P, lane);
+            const unsigned long long want = n > P.chunk ? n : P.chunk;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.cursor, want);
+            base = __shfl_sync(FULL, base, 0);
+            w_cur = base;
+            w_end = base + want;
+            blk_off = base;
+            blk_cnt = 0;
+        }
+        const unsigned long long at = w_cur;
+        w_cur += n;
+        blk_cnt += n;
+        total += n;
+        return at;
+    }
+    __device__ __forceinline__ void end(const FastParams& P, int lane) {
+        close_block(P, lane);
+        if (lane == 0) P.tile_cnt[strip] = total;
+    }
+};
 
 typedef void (*stream_kernel_t)(const FastParams);
 

@@ -10,19 +10,20 @@
 // A[r][j] > A[r-1][j] and A[r-1][j] >= p, provided no E decreases down a column
 // (matching statistics).  Only rows in which some E moved can emit.
 //
-// Every warp is an independent stream over its own tiles (tile = T consecutive
-// rows + the predecessor row, fetched by one bulk async copy into the warp's
-// private multi-stage shared-memory ring).  Tile bases are multiples of RPL rows
-// of the buffer, which makes them 16-byte aligned, so that
+// Every warp is an independent stream: it takes strips of G consecutive tiles
+// from an atomic counter (tile = T consecutive rows + the predecessor row, fetched
+// by one bulk async copy into the warp's private multi-stage shared-memory ring).
+// Tile bases are multiples of RPL rows of the buffer, which makes them 16-byte
+// aligned, so that
 //   phase A  a lane scans RPL consecutive rows with 128-bit shared-memory loads
 //            (lane stride RPL*CT*4 bytes = an odd number of 16-byte units: no
 //            bank conflicts) and flags the rows where v[r][c] != v[r-1][c] - 1,
 //   phase B  one lane per flagged row sorts the row and its predecessor with a
 //            register sorting network (--order), compares them position by
-//            position and stores the index rows straight into the tile's block
-//            of the scratch area (block obtained with one atomicAdd per tile;
-//            tile_scan_kernel / tile_gather_kernel of index_build.cu order the
-//            blocks afterwards).
+//            position and stores the index rows straight into the scratch area,
+//            appended to the strip's output (StripOut: the warp reserves scratch
+//            rows in chunks; tile_scan_kernel / strip_gather_kernel of
+//            index_build.cu copy the strips' blocks into the ordered output).
 // No warp ever waits for another.
 #include "index_fast.cuh"
 
@@ -77,34 +78,58 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     TileDesc* const descs = (TileDesc*)(wbase + P.off_descs);
     uint16_t* const list = (uint16_t*)(wbase + P.off_list);
 
-    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long w_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-
-    // fetch tile `tile` into stage s (lane 0 only); the record run of the previous
-    // tile is kept in registers, consecutive tiles of a warp mostly share it
-    long long c_lo = 0, c_hi = 0;
+    // ---------------- producer state (lane 0): the tile sequence of the warp's strips
+    const int G = P.R;                    // tiles per strip
+    long long c_lo = 0, c_hi = 0;         // strips of the cached record run
     memo_segment_t seg;
     seg.row_begin = seg.n_rows = 0;
     seg.pos0 = seg.rec_len = seg.rec_id = seg.flags = 0;
-    auto issue = [&](int s, long long tile) {
+    unsigned long long look = 0;          // next strip (fetched one strip ahead: hides the atomic)
+    long long p_strip = 0, p_tile = 0, p_left = 0, p_ntiles = 0;
+    bool p_first = false, p_done = false;
+    if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
+
+    // fetch the next tile into stage s (lane 0 only)
+    auto issue = [&](int s) {
+        if (p_done) return;
         uint64_t* bar = &bars[s];
-        if (tile >= P.n_tiles) return;
-        if (tile < c_lo || tile >= c_hi) {
-            int s_lo = 0, s_hi = P.n_seg - 1;
-            while (s_lo < s_hi) {
-                const int mid = (s_lo + s_hi + 1) >> 1;
-                if (P.seg_tile_start[mid] <= tile) s_lo = mid; else s_hi = mid - 1;
+        TileDesc d;
+        if (p_left == 0) {
+            p_strip = (long long)look;
+            if (p_strip >= P.n_tiles) {
+                d.n = 0; d.off = 0; d.pos_h = 0; d.rec_len = 0; d.flags = WD_END; d.r_lo = 1; d.r_hi = 0; d.pad = 0;
+                descs[s] = d;
+                mbar_arrive(bar);
+                p_done = true;
+                return;
             }
-            c_lo = P.seg_tile_start[s_lo];
-            c_hi = P.seg_tile_start[s_lo + 1];
-            seg = P.segs[s_lo];
+            look = atomicAdd(P.strip_counter, 1ull);
+            if (p_strip < c_lo || p_strip >= c_hi) {
+                int s_lo = 0, s_hi = P.n_seg - 1;
+                while (s_lo < s_hi) {
+                    const int mid = (s_lo + s_hi + 1) >> 1;
+                    if (P.seg_tile_start[mid] <= p_strip) s_lo = mid; else s_hi = mid - 1;
+                }
+                c_lo = P.seg_tile_start[s_lo];
+                c_hi = P.seg_tile_start[s_lo + 1];
+                seg = P.segs[s_lo];
+            }
+            // tiles of the run: see make_fast_plan
+            const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
+            const long long fc = seg.row_begin + primed, lc = seg.row_begin + seg.n_rows - 1;
+            const long long g = ((fc - 1) / RPL) * RPL;
+            long long nt = lc >= fc ? (lc - g + T - 1) / T : 0;
+            if (nt < 1) nt = 1;
+            p_ntiles = nt;
+            p_tile = (p_strip - c_lo) * G;
+            p_left = nt - p_tile < G ? nt - p_tile : G;
+            p_first = true;
         }
-        const long long t = tile - c_lo;
         const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
         const long long fc = seg.row_begin + primed;              // first / last compare row (buffer rows)
         const long long lc = seg.row_begin + seg.n_rows - 1;
         const long long g = ((fc - 1) / RPL) * RPL;               // aligned base of the run's first tile
-        const long long B = g + t * T;                            // buffer row of the tile's row 0
+        const long long B = g + p_tile * T;                       // buffer row of the tile's row 0
         const long long lo = (fc > B + 1 ? fc : B + 1) - B;
         const long long hi = (lc < B + T ? lc : B + T) - B;
         const long long a0 = B * (long long)CT * 4;               // 16-byte aligned
@@ -113,12 +138,13 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         long long a1 = (end + 15) & ~15ll;
         const long long lim = P.total_bytes & ~15ll;
         if (a1 > lim) a1 = lim;
-        TileDesc d;
+        const bool runlast = p_tile + 1 == p_ntiles;
         d.n = T;
-        d.off = 0;
+        d.off = (int)p_strip;
         d.pos_h = (uint32_t)seg.pos0 + (uint32_t)(B - seg.row_begin);
         d.rec_len = (uint32_t)seg.rec_len;
-        d.flags = ((tile + 1 == c_hi) ? 1 : 0) | ((seg.flags & MEMO_SEG_CHR_END) ? 2 : 0);
+        d.flags = (p_first ? WD_FIRST : 0) | (p_left == 1 ? WD_LAST : 0) | (runlast ? WD_RUNLAST : 0) |
+                  ((runlast && (seg.flags & MEMO_SEG_CHR_END)) ? WD_CHR : 0);
         d.r_lo = (int)lo;
         d.r_hi = (int)hi;
         d.pad = (int)(lc - B);                                    // tile row of the run's last row
@@ -126,7 +152,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         unsigned char* data = wbase + (size_t)s * P.stage_bytes;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.dap);
         // the last < 16 bytes of the buffer cannot be part of a 16-byte granular bulk copy
-        for (long long b = a1; b < end; b += 4)
+        for (long long b = (a1 > a0 ? a1 : a0); b < end; b += 4)
             *reinterpret_cast<uint32_t*>(data + (b - a0)) = *reinterpret_cast<const uint32_t*>(src + b);
         if (a1 > a0) {
             mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));
@@ -134,6 +160,9 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         } else {
             mbar_arrive(bar);
         }
+        ++p_tile;
+        --p_left;
+        p_first = false;
     };
 
     if (lane == 0) {
@@ -143,17 +172,19 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     }
     __syncwarp();
     if (lane == 0)
-        for (int s = 0; s < S; ++s) issue(s, w_global + (long long)s * n_warps);
+        for (int s = 0; s < S; ++s) issue(s);
 
     uint32_t irr_acc = 0;
     int s = 0;
     uint32_t parity = 0;
-    unsigned long long w_cur = 0, w_end = 0;          // the warp's reserved scratch rows
+    StripOut so;                                      // the strip's output blocks
     uint32_t* const ecol = reinterpret_cast<uint32_t*>(wbase + P.off_stg) + lane * (CT | 1);
 
-    for (long long tile = w_global; tile < P.n_tiles; tile += n_warps) {
+    for (;;) {
         mbar_wait(&bars[s], parity);
         const TileDesc d = descs[s];
+        if (d.flags & WD_END) break;
+        if (d.flags & WD_FIRST) so.begin(d.off);
         const uint32_t* const sdata = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes);
 
         // ---------------- phase A: ordered list of the live rows that moved a MEM end
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
                 n_ch += total;
             }
         }
-        if ((d.flags & 3) == 3) {                       // the chr-end rows after the run's last row
+        if (d.flags & WD_CHR) {                         // the chr-end rows after the run's last row
             if (lane == 0) list[n_ch] = (uint16_t)(0x8000 | (d.pad + 1));
             ++n_ch;
         }
@@ -247,7 +278,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
                 cnt += __popc(row_rows(ps * 32 + lane, e, p, lim));
             }
             tile_total = __reduce_add_sync(FULL, cnt);
-            if (tile_total) base = warp_alloc(P, w_cur, w_end, tile_total, lane);
+            if (tile_total) base = so.reserve(P, tile_total, lane);
         }
         uint32_t running = 0;
         for (int ps = 0; ps < n_pass; ++ps) {
@@ -263,7 +294,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
             const uint32_t total = __shfl_sync(FULL, incl, 31);
             if (n_pass == 1) {
                 tile_total = total;
-                if (total) base = warp_alloc(P, w_cur, w_end, total, lane);
+                if (total) base = so.reserve(P, total, lane);
             }
             // the lane's index rows: its emitting positions in ascending order.  The
             // (sorted) ends go through the lane's shared-memory column so that the loop
@@ -283,12 +314,9 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
             }
             running += total;
         }
-        if (lane == 0) {
-            P.tile_cnt[tile] = tile_total;
-            P.tile_off[tile] = base;
-        }
+        if (d.flags & WD_LAST) so.end(P, lane);
         __syncwarp();                    // stage s and the list are free again
-        if (lane == 0) issue(s, tile + (long long)S * n_warps);
+        if (lane == 0) issue(s);
         if (++s == S) {
             s = 0;
             parity ^= 1u;

@@ -33,11 +33,6 @@
 namespace memo {
 namespace {
 
-constexpr int WD_FIRST = 1;    // chunk row 0 is the strip's predecessor row
-constexpr int WD_LAST = 2;     // last chunk of the strip
-constexpr int WD_CHR = 4;      // chr-end rows follow the strip
-constexpr int WD_END = 8;      // no more strips
-
 template <int KPL, bool ORDER>
 __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -154,37 +149,8 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
     uint32_t A[KPL];                   // ORDER: sorted MEM ends of the previous row, position ibase + k
 #pragma unroll
     for (int k = 0; k < KPL; ++k) prv[k] = A[k] = 0;
-    unsigned long long w_cur = 0, w_end = 0;       // the warp's reserved scratch rows
-    unsigned long long blk_off = 0;                // open block of the strip
-    uint32_t blk_cnt = 0, strip_total = 0;
-    int nblk = 0, last_rec = -1;                   // blocks closed so far; pool index of the last one
-    long long strip = 0;
+    StripOut so;                       // the strip's output blocks
     uint32_t irr_acc = 0;
-
-    // close the strip's open block: the first one is described by the strip's own
-    // entries, later ones by pool records chained from it
-    auto close_block = [&]() {
-        if (nblk == 0) {
-            if (lane == 0) {
-                P.tile_off[strip] = blk_off;
-                P.first_cnt[strip] = blk_cnt;
-                P.unit_next[strip] = -1;
-            }
-        } else {
-            int idx = 0;
-            if (lane == 0) {
-                idx = (int)atomicAdd(P.pool_counter, 1u);
-                if ((uint32_t)idx < P.pool_cap) {
-                    BlockRec rec;
-                    rec.off = blk_off; rec.cnt = blk_cnt; rec.next = -1;
-                    P.pool[idx] = rec;
-                    if (nblk == 1) P.unit_next[strip] = idx; else P.pool[last_rec].next = idx;
-                }
-            }
-            last_rec = __shfl_sync(FULL, idx, 0);
-        }
-        ++nblk;
-    };
 
     // index rows of one row: em[k] / endv[k] per slot, `p` = BED start.  Output
     // order: ORDER -> position ibase + k; else column lane + 32 k.
@@ -197,18 +163,9 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
             total += __popc(b[k]);
         }
         if (total == 0) return;
-        if (total > w_end - w_cur) {               // next chunk: the strip continues in a new block
-            close_block();
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.cursor, (unsigned long long)P.chunk);
-            base = __shfl_sync(FULL, base, 0);
-            w_cur = base;
-            w_end = base + P.chunk;
-            blk_off = base;
-            blk_cnt = 0;
-        }
-        if (w_cur + total <= (unsigned long long)P.scr_cap) {
-            uint32_t* const dst0 = P.scr + w_cur * 3;          // warp uniform
+        const unsigned long long at = so.reserve(P, total, lane);
+        if (at + total <= (unsigned long long)P.scr_cap) {
+            uint32_t* const dst0 = P.scr + at * 3;             // warp uniform
             if (ORDER) {
 #pragma unroll
                 for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
@@ -225,9 +182,6 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                 if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
             }
         }
-        w_cur += total;
-        blk_cnt += total;
-        strip_total += total;
     };
 
     int s = 0;
@@ -249,11 +203,7 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                 for (int k = 0; k < KPL; ++k) A[k] = cvalid[k] ? prv[k] + pos : 0u;
                 group_sort_desc<32, KPL>(A, lane);
             }
-            strip = d.r_lo;
-            nblk = 0;
-            blk_off = w_cur;
-            blk_cnt = 0;
-            strip_total = 0;
+            so.begin(d.r_lo);
             lp += ld;
             ++pos;
             --left;
@@ -349,8 +299,7 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                 }
                 emit(em, endv, d.rec_len);
             }
-            close_block();
-            if (lane == 0) P.tile_cnt[strip] = strip_total;
+            so.end(P, lane);
         }
         __syncwarp();                    // stage s is free again
         if (lane == 0) issue(s);

@@ -20,7 +20,7 @@ import torch
 from . import api
 from ._lib import MemoError, RES_IRREGULAR, RES_N_OUT, RES_SLOTS
 
-DEFAULT_CHUNK_BYTES = 64 << 20
+DEFAULT_CHUNK_BYTES = 256 << 20
 RING = 3
 
 _pinned_pool = {}
