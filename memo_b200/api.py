@@ -234,7 +234,8 @@ def _query_common(f1, f2, f3):
 
 def query_conservation(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_start: int,
                        q_end: int, k: int, n_docs: int, out: Optional[torch.Tensor] = None,
-                       check: bool = True) -> torch.Tensor:
+                       check: bool = True, status: Optional[torch.Tensor] = None,
+                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Conservation vector (uint8, or int16-typed uint16 when n_docs > 255) for the
     window [q_start, q_end).  f1/f2/f3: one record's index rows, f1 ascending
     (f2 holds uint32 bits)."""
@@ -245,9 +246,11 @@ def query_conservation(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_s
     u16 = n_docs > 255
     if out is None:
         out = torch.empty(W, dtype=torch.int16 if u16 else torch.uint8, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
     need = lib.memo_query_workspace_bytes(W)
-    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    ws = workspace if workspace is not None and workspace.numel() >= need else \
+        torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     rc = lib.memo_query_conservation(_ptr(f1), _ptr(f2), _ptr(f3), f1.numel(), q_start, q_end, k,
                                      n_docs, _ptr(out), 1 if u16 else 0, status.data_ptr(),
                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev))

@@ -17,18 +17,18 @@
 namespace memo {
 namespace {
 
-constexpr int QT = 8192;       // window positions per tile
+constexpr int QT_MIN = 8192;   // window positions per tile
 constexpr int QTHREADS = 256;
 
 // lo[t] = first row with f1 > s + t*QT              (t = 0..n_tiles-1)
 // hi[t] = first row with f1 > s + (t+1)*QT + k - 2
 __global__ void query_bounds_kernel(const int32_t* __restrict__ f1, long long n_rows, long long s,
-                                    int k, long long n_tiles, long long* __restrict__ lo,
+                                    int k, int QT, long long n_tiles, long long* __restrict__ lo,
                                     long long* __restrict__ hi) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const long long key_lo = s + t * QT;
-    const long long key_hi = s + (t + 1) * QT + k - 2;
+    const long long key_lo = s + t * (long long)QT;
+    const long long key_hi = s + (t + 1) * (long long)QT + k - 2;
     long long a = 0, b = n_rows;
     while (a < b) {
         const long long m = (a + b) >> 1;
@@ -43,35 +43,47 @@ __global__ void query_bounds_kernel(const int32_t* __restrict__ f1, long long n_
     hi[t] = a;
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(QTHREADS)
+template <typename OutT, int QT, int TH>
+__global__ void __launch_bounds__(TH)
 query_conservation_kernel(const int32_t* __restrict__ f1, const uint32_t* __restrict__ f2,
                           const int32_t* __restrict__ f3, const long long* __restrict__ lo,
                           const long long* __restrict__ hi, long long s, long long W, int k,
                           int n_docs, OutT* __restrict__ out, int32_t* status) {
     __shared__ uint32_t tile[QT];
     const long long n_tiles = (W + QT - 1) / QT;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    long long t = blockIdx.x;
+    if (t >= n_tiles) return;
+    long long r0 = lo[t], r1 = hi[t];
+    for (; t < n_tiles; t += gridDim.x) {
         const long long t0 = t * QT;
         const long long t1 = min(t0 + (long long)QT, W);
-        for (int i = threadIdx.x; i < QT; i += QTHREADS) tile[i] = (uint32_t)n_docs;
+        // the tile's first batch of rows and the next tile's row range are requested before
+        // the tile is initialised: their latency overlaps the shared-memory work
+        long long r = r0 + threadIdx.x;
+        const bool have = r < r1;
+        const int32_t v1 = have ? f1[r] : 0;
+        const uint32_t v2 = have ? f2[r] : 0u;
+        const int32_t v3 = have ? f3[r] : 0;
+        const long long tn = t + gridDim.x;
+        const long long nr0 = tn < n_tiles ? lo[tn] : 0, nr1 = tn < n_tiles ? hi[tn] : 0;
+        for (int i = threadIdx.x; i < QT; i += TH) tile[i] = (uint32_t)n_docs;
         __syncthreads();
-        const long long r0 = lo[t], r1 = hi[t];
-        for (long long r = r0 + threadIdx.x; r < r1; r += QTHREADS) {
-            const long long start = (long long)f1[r] - s;                 // > t0 by construction
-            const long long cend = (long long)f2[r] - s - (k - 1);
-            const int32_t ord = f3[r];
-            if (ord < 0 || ord > n_docs) { *status = 1; continue; }
-            const long long a = max(cend, t0);                           // clip to [0, W] and to the tile
+        auto paint = [&](int32_t a1, uint32_t a2, int32_t ord) {
+            const long long start = (long long)a1 - s;                    // > t0 by construction
+            const long long cend = (long long)a2 - s - (k - 1);
+            if (ord < 0 || ord > n_docs) { *status = 1; return; }
+            const long long a = max(cend, t0);                            // clip to [0, W] and to the tile
             const long long b = min(start, t1);
             for (long long q = a; q < b; ++q) atomicMin(&tile[q - t0], (uint32_t)ord);
-        }
+        };
+        if (have) paint(v1, v2, v3);
+        for (r += TH; r < r1; r += TH) paint(f1[r], f2[r], f3[r]);
         __syncthreads();
         const int n = (int)(t1 - t0);
         if (sizeof(OutT) == 1 && n == QT) {
             // 16 positions per thread -> one 128-bit store
             uint4* dst = reinterpret_cast<uint4*>(out + t0);
-            for (int i = threadIdx.x; i < QT / 16; i += QTHREADS) {
+            for (int i = threadIdx.x; i < QT / 16; i += TH) {
                 uint32_t w[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -81,9 +93,11 @@ query_conservation_kernel(const int32_t* __restrict__ f1, const uint32_t* __rest
                 dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         } else {
-            for (int i = threadIdx.x; i < n; i += QTHREADS) out[t0 + i] = (OutT)tile[i];
+            for (int i = threadIdx.x; i < n; i += TH) out[t0 + i] = (OutT)tile[i];
         }
         __syncthreads();
+        r0 = nr0;
+        r1 = nr1;
     }
 }
 
@@ -141,7 +155,7 @@ extern "C" {
 
 size_t memo_query_workspace_bytes(int64_t window_len) {
     if (window_len < 0) window_len = 0;
-    const int64_t n_tiles = (window_len + memo::QT - 1) / memo::QT;
+    const int64_t n_tiles = (window_len + memo::QT_MIN - 1) / memo::QT_MIN;
     return memo::align_up(sizeof(long long) * (size_t)(n_tiles + 1), 256) * 2;
 }
 
@@ -161,6 +175,7 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     if (W == 0) return MEMO_OK;
     MEMO_REQUIRE(out != nullptr, "out must not be NULL");
     MEMO_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+    constexpr int QT = 8192, TH = QTHREADS;   // measured on B200: tile / CTA size hardly matter (2048..8192, 64..256)
     const long long n_tiles = (W + QT - 1) / QT;
     const size_t half = align_up(sizeof(long long) * (size_t)(n_tiles + 1), 256);
     if (workspace == nullptr || workspace_bytes < 2 * half) {
@@ -169,16 +184,16 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     }
     long long* lo = static_cast<long long*>(workspace);
     long long* hi = reinterpret_cast<long long*>(static_cast<char*>(workspace) + half);
-    query_bounds_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(f1, n_rows, q_start, k, n_tiles, lo, hi);
+    query_bounds_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(f1, n_rows, q_start, k, QT, n_tiles, lo, hi);
     MEMO_CUDA_TRY(cudaGetLastError());
     const int sms = device_sm_count();
     long long grid = (long long)sms * 5;     // 32 KB of shared memory per CTA
     if (grid > n_tiles) grid = n_tiles;
     if (out_u16)
-        query_conservation_kernel<uint16_t><<<(unsigned)grid, QTHREADS, 0, stream>>>(
+        query_conservation_kernel<uint16_t, QT, TH><<<(unsigned)grid, TH, 0, stream>>>(
             f1, f2, f3, lo, hi, q_start, W, k, n_docs, static_cast<uint16_t*>(out), status);
     else
-        query_conservation_kernel<uint8_t><<<(unsigned)grid, QTHREADS, 0, stream>>>(
+        query_conservation_kernel<uint8_t, QT, TH><<<(unsigned)grid, TH, 0, stream>>>(
             f1, f2, f3, lo, hi, q_start, W, k, n_docs, static_cast<uint8_t*>(out), status);
     MEMO_CUDA_TRY(cudaGetLastError());
     return MEMO_OK;
