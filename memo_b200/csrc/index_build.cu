@@ -289,8 +289,10 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     // every chunk a strip crosses into costs one BlockRec
     plan->pool_cap = (uint32_t)(plan->scr_cap / (chunk / 2) + max_warps + 16);
 
-    // a warp's stages must fit its share of the SM's shared memory
-    const long long budget = (220 * 1024 / plan->warps - 1024) / plan->stages;
+    // a warp's stages must fit its share of the SM's shared memory (next to its queue of
+    // flagged rows, row list, barriers and descriptors)
+    const long long queue_bytes = plan->narrow ? 4 * 40 * (long long)((2 * C + 2) | 1) : 0;   // NARROW_QCAP entries
+    const long long budget = (220 * 1024 / plan->warps - 1024 - queue_bytes - 2 * (MAX_TILE_ROWS + 4)) / plan->stages;
     long long T;
     size_t extra = 0;
     if (plan->narrow) {
@@ -306,7 +308,7 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         if (G < 1) G = 1;
         plan->R = (int)G;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
-        extra = 4 * 32 * (size_t)(C | 1) + 2 * (size_t)(T + 4);       // end columns + row list
+        extra = 0;
     } else {
         // strips of R rows stream through the ring in chunks of T rows (~3.75 KB)
         T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 3840 / row_bytes;
@@ -323,7 +325,7 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     size_t o = (size_t)plan->stages * plan->stage_bytes;
     plan->off_bars = (uint32_t)o;    o += 8 * MAX_STAGES;
     plan->off_descs = (uint32_t)o;   o += sizeof(TileDesc) * MAX_STAGES;
-    plan->off_stg = (uint32_t)o;     o += plan->narrow ? 4 * 32 * (size_t)(C | 1) : 0;
+    plan->off_stg = (uint32_t)o;     o += (size_t)queue_bytes;
     plan->off_list = (uint32_t)o;    o += plan->narrow ? 2 * (size_t)(T + 4) : 0;
     (void)extra;
     plan->warp_smem = (uint32_t)align_up(o, 128);

@@ -18,17 +18,23 @@
 //   phase A  a lane scans RPL consecutive rows with 128-bit shared-memory loads
 //            (lane stride RPL*CT*4 bytes = an odd number of 16-byte units: no
 //            bank conflicts) and flags the rows where v[r][c] != v[r-1][c] - 1,
-//   phase B  one lane per flagged row sorts the row and its predecessor with a
-//            register sorting network (--order), compares them position by
-//            position and stores the index rows straight into the scratch area,
-//            appended to the strip's output (StripOut: the warp reserves scratch
-//            rows in chunks; tile_scan_kernel / strip_gather_kernel of
-//            index_build.cu copy the strips' blocks into the ordered output).
+//   phase B  the flagged rows (a few per tile) are queued in shared memory as
+//            (start, limit, MEM ends of the predecessor row, MEM ends of the row);
+//            whenever 32 are waiting -- or the strip ends -- one lane per queued
+//            row sorts both with a register sorting network (--order), compares
+//            them position by position and stores the index rows straight into
+//            the scratch area, appended to the strip's output (StripOut: the warp
+//            reserves scratch rows in chunks; tile_scan_kernel /
+//            strip_gather_kernel of index_build.cu copy the strips' blocks into
+//            the ordered output).  The sorting network thus always runs on a full
+//            warp, not on the handful of rows one tile flags.
 // No warp ever waits for another.
 #include "index_fast.cuh"
 
 namespace memo {
 namespace {
+
+constexpr int NARROW_QCAP = 40;        // queued flagged rows per warp (>= 32 + what one more append leaves)
 
 __host__ __device__ constexpr int gcd4(int c) { return (c % 4 == 0) ? 4 : ((c % 2 == 0) ? 2 : 1); }
 
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     seg.row_begin = seg.n_rows = 0;
     seg.pos0 = seg.rec_len = seg.rec_id = seg.flags = 0;
     unsigned long long look = 0;          // next strip (fetched one strip ahead: hides the atomic)
-    long long p_strip = 0, p_tile = 0, p_left = 0, p_ntiles = 0;
+    long long p_strip = 0, p_tile = 0, p_left = 0, p_ntiles = 0, p_fc = 0, p_lc = 0, p_B = 0;
     bool p_first = false, p_done = false;
     if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
 
@@ -116,24 +122,23 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
             }
             // tiles of the run: see make_fast_plan
             const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
-            const long long fc = seg.row_begin + primed, lc = seg.row_begin + seg.n_rows - 1;
-            const long long g = ((fc - 1) / RPL) * RPL;
-            long long nt = lc >= fc ? (lc - g + T - 1) / T : 0;
+            p_fc = seg.row_begin + primed;                        // first / last compare row (buffer rows)
+            p_lc = seg.row_begin + seg.n_rows - 1;
+            const long long g = ((p_fc - 1) / RPL) * RPL;         // aligned base of the run's first tile
+            long long nt = p_lc >= p_fc ? (p_lc - g + T - 1) / T : 0;
             if (nt < 1) nt = 1;
             p_ntiles = nt;
             p_tile = (p_strip - c_lo) * G;
             p_left = nt - p_tile < G ? nt - p_tile : G;
+            p_B = g + p_tile * T;                                 // buffer row of the next tile's row 0
             p_first = true;
         }
-        const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
-        const long long fc = seg.row_begin + primed;              // first / last compare row (buffer rows)
-        const long long lc = seg.row_begin + seg.n_rows - 1;
-        const long long g = ((fc - 1) / RPL) * RPL;               // aligned base of the run's first tile
-        const long long B = g + p_tile * T;                       // buffer row of the tile's row 0
-        const long long lo = (fc > B + 1 ? fc : B + 1) - B;
-        const long long hi = (lc < B + T ? lc : B + T) - B;
-        const long long a0 = B * (long long)CT * 4;               // 16-byte aligned
-        long long end = (B + T + 1) * (long long)CT * 4;
+        const long long B = p_B;
+        const long long lo = (p_fc > B + 1 ? p_fc : B + 1) - B;
+        const long long hi = (p_lc < B + T ? p_lc : B + T) - B;
+        const long long lc = p_lc;
+        const long long a0 = B * (long long)(CT * 4);             // 16-byte aligned
+        long long end = a0 + (long long)(T + 1) * (CT * 4);
         if (end > P.total_bytes) end = P.total_bytes;
         long long a1 = (end + 15) & ~15ll;
         const long long lim = P.total_bytes & ~15ll;
@@ -162,6 +167,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         }
         ++p_tile;
         --p_left;
+        p_B += T;
         p_first = false;
     };
 
@@ -178,7 +184,66 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     int s = 0;
     uint32_t parity = 0;
     StripOut so;                                      // the strip's output blocks
-    uint32_t* const ecol = reinterpret_cast<uint32_t*>(wbase + P.off_stg) + lane * (CT | 1);
+    // queue of flagged rows (ring): entry = {start, limit, e[CT], f[CT]}, odd stride
+    constexpr int ESTR = (2 * CT + 2) | 1;
+    constexpr int QCAP = NARROW_QCAP;
+    uint32_t* const queue = reinterpret_cast<uint32_t*>(wbase + P.off_stg);
+    int qhead = 0, qn = 0;
+
+    // phase B on the first n (<= 32) queued rows: one lane per row
+    auto flush = [&](int n) {
+        uint32_t e[CT], p = 0, lim = 0;
+        unsigned m = 0;
+        int slot = qhead + lane;
+        if (slot >= QCAP) slot -= QCAP;
+        uint32_t* const q = queue + slot * ESTR;
+        if (lane < n) {
+            uint32_t f[CT];
+            p = q[0];
+            lim = q[1];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                e[c] = q[2 + c];
+                f[c] = q[2 + CT + c];
+            }
+            if (ORDER) {
+                sort_desc_network<CT>(e);
+                sort_desc_network<CT>(f);
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) m |= (f[c] > e[c] && e[c] >= p) ? (1u << c) : 0u;
+            // the (sorted) ends go back into the entry: the store loop below then runs
+            // once per emitted row, not once per column
+#pragma unroll
+            for (int c = 0; c < CT; ++c) q[2 + c] = min(e[c], lim);
+        }
+        const uint32_t cnt = __popc(m);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (total) {
+            const unsigned long long base = so.reserve(P, total, lane);
+            unsigned long long gi = base + (incl - cnt);
+            unsigned mm = (gi + cnt <= (unsigned long long)P.scr_cap) ? m : 0u;
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                uint32_t* dst = P.scr + gi * 3;
+                dst[0] = p;
+                dst[1] = q[2 + c];
+                dst[2] = (uint32_t)(c + 1);
+                ++gi;
+            }
+        }
+        __syncwarp();
+        qhead += n;
+        if (qhead >= QCAP) qhead -= QCAP;
+        qn -= n;
+    };
 
     for (;;) {
         mbar_wait(&bars[s], parity);
@@ -240,79 +305,35 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         }
         __syncwarp();
 
-        // ---------------- phase B: one lane per listed row
-        // e[] = (sorted) MEM ends of the predecessor row; returns the bitmap of the
-        // sorted positions / columns that emit an index row
-        auto row_rows = [&](int idx, uint32_t (&e)[CT], uint32_t& p, uint32_t& lim) -> unsigned {
-            const bool act = idx < n_ch;
-            const unsigned ent = act ? list[idx] : 1u;
-            const bool chr = (ent & 0x8000u) != 0u;
-            const int row = (int)(ent & 0x7FFFu);
-            const uint32_t* prevp = sdata + (row - 1) * CT;
-            const uint32_t ppos = d.pos_h + (uint32_t)(row - 1);
-            p = chr ? d.rec_len : ppos + 1u;
-            lim = chr ? 2u * d.rec_len : 0xFFFFFFFFu;
-            uint32_t f[CT];
+        // ---------------- queue the listed rows; phase B whenever a full warp of them waits
+        for (int done = 0; done < n_ch;) {
+            int m = n_ch - done;
+            if (m > 32) m = 32;
+            if (m > QCAP - qn) m = QCAP - qn;
+            if (lane < m) {
+                const unsigned ent = list[done + lane];
+                const bool chr = (ent & 0x8000u) != 0u;
+                const int row = (int)(ent & 0x7FFFu);
+                const uint32_t* prevp = sdata + (row - 1) * CT;
+                const uint32_t ppos = d.pos_h + (uint32_t)(row - 1);
+                int slot = qhead + qn + lane;
+                if (slot >= QCAP) slot -= QCAP;
+                uint32_t* q = queue + slot * ESTR;
+                q[0] = chr ? d.rec_len : ppos + 1u;
+                q[1] = chr ? 2u * d.rec_len : 0xFFFFFFFFu;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                e[c] = prevp[c] + ppos;
-                f[c] = chr ? 0xFFFFFFFFu : prevp[CT + c] + ppos + 1u;
+                for (int c = 0; c < CT; ++c) {
+                    q[2 + c] = prevp[c] + ppos;
+                    q[2 + CT + c] = chr ? 0xFFFFFFFFu : prevp[CT + c] + ppos + 1u;
+                }
             }
-            if (ORDER) {
-                sort_desc_network<CT>(e);
-                sort_desc_network<CT>(f);
-            }
-            unsigned m = 0;
-#pragma unroll
-            for (int c = 0; c < CT; ++c) m |= (f[c] > e[c] && e[c] >= p) ? (1u << c) : 0u;
-            return act ? m : 0u;
-        };
-
-        const int n_pass = (n_ch + 31) >> 5;
-        unsigned long long base = 0;
-        uint32_t tile_total = 0;
-        if (n_pass > 1) {                               // dense tile: count first, the block must be contiguous
-            uint32_t cnt = 0;
-            for (int ps = 0; ps < n_pass; ++ps) {
-                uint32_t e[CT], p, lim;
-                cnt += __popc(row_rows(ps * 32 + lane, e, p, lim));
-            }
-            tile_total = __reduce_add_sync(FULL, cnt);
-            if (tile_total) base = so.reserve(P, tile_total, lane);
+            qn += m;
+            done += m;
+            __syncwarp();
+            if (qn >= 32) flush(32);
         }
-        uint32_t running = 0;
-        for (int ps = 0; ps < n_pass; ++ps) {
-            uint32_t e[CT], p, lim;
-            const unsigned m = row_rows(ps * 32 + lane, e, p, lim);
-            const uint32_t cnt = __popc(m);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            if (n_pass == 1) {
-                tile_total = total;
-                if (total) base = so.reserve(P, total, lane);
-            }
-            // the lane's index rows: its emitting positions in ascending order.  The
-            // (sorted) ends go through the lane's shared-memory column so that the loop
-            // runs once per emitted row, not once per column.
-            unsigned long long gi = base + running + (incl - cnt);
-#pragma unroll
-            for (int c = 0; c < CT; ++c) ecol[c] = min(e[c], lim);
-            unsigned mm = (gi + cnt <= (unsigned long long)P.scr_cap) ? m : 0u;
-            while (mm) {
-                const int c = __ffs(mm) - 1;
-                mm &= mm - 1;
-                uint32_t* dst = P.scr + gi * 3;
-                dst[0] = p;
-                dst[1] = ecol[c];
-                dst[2] = (uint32_t)(c + 1);
-                ++gi;
-            }
-            running += total;
+        if (d.flags & WD_LAST) {
+            while (qn > 0) flush(qn < 32 ? qn : 32);
         }
         if (d.flags & WD_LAST) so.end(P, lane);
         __syncwarp();                    // stage s and the list are free again
