@@ -222,44 +222,78 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                 bool em[KPL];
                 uint32_t endv[KPL];
                 if (ORDER) {
-                    uint32_t Aold[KPL];
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) Aold[k] = A[k];
-                    // cells whose MEM end moved up, one per lane and round (a decrease makes
-                    // the input irregular: flagged through irr_acc, skipped here)
-                    unsigned todo = 0;
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) todo |= ((int)(dk[k] & vm[k]) > 0) ? (1u << k) : 0u;
-                    unsigned m;
-                    while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
-                        uint32_t myx = 0, myd = 0;
-#pragma unroll
-                        for (int k = KPL - 1; k >= 0; --k)
-                            if (todo & (1u << k)) { myx = prev[k]; myd = dk[k]; }
-                        todo &= todo - 1;
-                        do {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            // delete x, insert y > x: the positions holding x <= A <= y shift
-                            // down by one and y lands on the first of them
-                            const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
-                            const uint32_t y = x + __shfl_sync(FULL, myd, src);
-                            uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
-                            if (lane == 0) up = 0xFFFFFFFFu;
-                            uint32_t nA[KPL];
-#pragma unroll
-                            for (int kk = 0; kk < KPL; ++kk) {
-                                const uint32_t before = kk == 0 ? up : A[kk - 1];
-                                nA[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
-                            }
-#pragma unroll
-                            for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
-                        } while (m);
-                    }
+                    // cells whose MEM end moved up (a decrease makes the input irregular:
+                    // flagged through irr_acc, skipped here)
+                    unsigned bk[KPL], ball = 0;
+                    int nchg = 0;
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) {
-                        em[k] = A[k] > Aold[k] && Aold[k] >= pos && ibase + k < C;
-                        endv[k] = Aold[k];
+                        bk[k] = __ballot_sync(FULL, (int)(k == KPL - 1 ? (dk[k] & vm[k]) : dk[k]) > 0);
+                        ball |= bk[k];
+                        nchg += __popc(bk[k]);
+                    }
+                    if (nchg == 1) {
+                        // the common case, one cell x -> y: the positions holding x <= A <= y
+                        // shift down by one, y lands on the first of them, and exactly those
+                        // positions can emit
+                        uint32_t myx = prev[0], myd = dk[0];
+#pragma unroll
+                        for (int k = 1; k < KPL; ++k)
+                            if (bk[k]) { myx = prev[k]; myd = dk[k]; }          // warp uniform
+                        const int src = __ffs(ball) - 1;
+                        const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
+                        const uint32_t y = x + __shfl_sync(FULL, myd, src);
+                        uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                        if (lane == 0) up = 0xFFFFFFFFu;
+                        uint32_t nA[KPL];
+#pragma unroll
+                        for (int kk = 0; kk < KPL; ++kk) {
+                            const uint32_t before = kk == 0 ? up : A[kk - 1];
+                            const bool inr = A[kk] >= x && A[kk] <= y;
+                            nA[kk] = inr ? min(before, y) : A[kk];
+                            em[kk] = inr && nA[kk] > A[kk] && A[kk] >= pos && ibase + kk < C;
+                            endv[kk] = A[kk];
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
+                    } else {
+                        uint32_t Aold[KPL];
+#pragma unroll
+                        for (int k = 0; k < KPL; ++k) Aold[k] = A[k];
+                        // one cell per lane and round
+                        unsigned todo = 0;
+#pragma unroll
+                        for (int k = 0; k < KPL; ++k) todo |= ((bk[k] >> lane) & 1u) << k;
+                        unsigned m;
+                        while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
+                            uint32_t myx = 0, myd = 0;
+#pragma unroll
+                            for (int k = KPL - 1; k >= 0; --k)
+                                if (todo & (1u << k)) { myx = prev[k]; myd = dk[k]; }
+                            todo &= todo - 1;
+                            do {
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                // delete x, insert y > x
+                                const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
+                                const uint32_t y = x + __shfl_sync(FULL, myd, src);
+                                uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                                if (lane == 0) up = 0xFFFFFFFFu;
+                                uint32_t nA[KPL];
+#pragma unroll
+                                for (int kk = 0; kk < KPL; ++kk) {
+                                    const uint32_t before = kk == 0 ? up : A[kk - 1];
+                                    nA[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
+                                }
+#pragma unroll
+                                for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
+                            } while (m);
+                        }
+#pragma unroll
+                        for (int k = 0; k < KPL; ++k) {
+                            em[k] = A[k] > Aold[k] && Aold[k] >= pos && ibase + k < C;
+                            endv[k] = Aold[k];
+                        }
                     }
                 } else {
 #pragma unroll
