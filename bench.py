@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0, help="index kernel variant (1 = strip kernel for narrow rows)")
+    ap.add_argument("--membership", action="store_true",
+                    help="membership index (-m: no --order) + membership query (BASELINE configs[2])")
     ap.add_argument("--env", action="append", default=[], help="KEY=VAL set before the library loads (tuning)")
     args = ap.parse_args()
     for kv in args.env:
@@ -249,11 +251,13 @@ def main():
     builder = api.IndexBuilder(dev)
     seg_out_end = torch.zeros(len(segs), dtype=torch.int64, device=dev)
     # size the outputs with a counting run
-    builder.launch(dap, C, segs, True, None, seg_out_end, **tuning)
+    order = not args.membership
+    builder.launch(dap, C, segs, order, None, seg_out_end, **tuning)
     n_all, irregular, _ = builder.result()
     assert not irregular, "synthetic DAP must be valid matching statistics"
     out = tuple(torch.empty(n_all + 16, dtype=torch.int32, device=dev) for _ in range(3))
-    q_out = torch.empty(Lr, dtype=torch.uint8, device=dev)
+    q_out = torch.empty((Lr, (n_docs + 31) // 32), dtype=torch.int32, device=dev) if args.membership \
+        else torch.empty(Lr, dtype=torch.uint8, device=dev)
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
     q_status = torch.zeros(1, dtype=torch.int32, device=dev)
     q_ws = torch.empty(max(_lib.load().memo_query_workspace_bytes(Lr), 1), dtype=torch.uint8, device=dev)
@@ -263,15 +267,19 @@ def main():
         # run (and re-checked after the timed region), the query reads the fresh rows
         if ev:
             ev[0].record()
-        builder.launch(dap, C, segs, True, out, seg_out_end, **tuning)
+        builder.launch(dap, C, segs, order, out, seg_out_end, **tuning)
         if ev:
             ev[1].record()
         if world > 1:                                 # ordered write offsets: gather the counts
             dist.all_gather_into_tensor(counts, seg_out_end[:1])
         if ev:
             ev[2].record()
-        api.query_conservation(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
-                               out=q_out, check=False, status=q_status, workspace=q_ws)
+        if args.membership:
+            api.query_membership(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
+                                 out=q_out, check=False, status=q_status)
+        else:
+            api.query_conservation(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
+                                   out=q_out, check=False, status=q_status, workspace=q_ws)
         if ev:
             ev[3].record()
 
@@ -310,9 +318,17 @@ def main():
     n_owned = int(seg_out_end[0].item())
 
     # correctness guard on the timed configuration: SURVEY 0.2 invariant
-    want = (1 + (dap[lo - buf_lo:hi - buf_lo] >= k).sum(dim=1)).to(torch.uint8)
-    assert torch.equal(q_out, want), "query result violates conservation == 1 + #{MS >= k}"
-    del want
+    if args.membership:
+        # membership[p] = [1, MS_1[p] >= k, ...]: compare a slice bit by bit
+        n_chk = min(Lr, 2_000_000)
+        bits = api.unpack_membership(q_out[:n_chk].cpu().numpy(), n_docs)
+        want = (dap[lo - buf_lo:lo - buf_lo + n_chk] >= k).cpu().numpy().astype(np.uint8)
+        assert bits[:, 0].all() and np.array_equal(bits[:, 1:], want), "membership != [1, MS >= k]"
+        del bits, want
+    else:
+        want = (1 + (dap[lo - buf_lo:hi - buf_lo] >= k).sum(dim=1)).to(torch.uint8)
+        assert torch.equal(q_out, want), "query result violates conservation == 1 + #{MS >= k}"
+        del want
 
     stats = torch.tensor([total_ms, idx_ms, qry_ms, float(n_owned), kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -327,7 +343,7 @@ def main():
 
     # ---------------- end-to-end leg: host buffers through the host API
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.membership:
         host_dap = torch.empty(tuple(dap.shape), dtype=torch.int32, pin_memory=True)
         host_dap.copy_(dap)
         h2d = d2h = 0
@@ -369,7 +385,7 @@ def main():
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not args.membership:
         cores = os.cpu_count() or 1
         sample = min(Lr, args.cpu_sample_rows)
         dap_np = dap[:sample].cpu().numpy()
@@ -392,11 +408,11 @@ def main():
         ach = bytes_idx / (kern_ms * 1e-3) / 1e9          # dominant kernel: the streaming kernel
         ach_build = bytes_idx / (idx_ms * 1e-3) / 1e9     # whole memo_index_build (stream + scan + gather)
         n_q_rows = n_all
-        bytes_q = 12.0 * n_q_rows + 1.0 * Lr
+        bytes_q = 12.0 * n_q_rows + (4.0 * ((n_docs + 31) // 32) if args.membership else 1.0) * Lr
         ach_q = bytes_q / (qry_ms * 1e-3) / 1e9
         value = Lr * world * args.steps / (total_ms * 1e-3)
         line = {
-            "metric": "pivot bp/s (conservation index build + k-mer query)",
+            "metric": "pivot bp/s (%s index build + k-mer query)" % ("membership" if args.membership else "conservation"),
             "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",

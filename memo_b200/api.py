@@ -262,7 +262,7 @@ def query_conservation(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_s
 
 def query_membership(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_start: int,
                      q_end: int, k: int, n_docs: int, out: Optional[torch.Tensor] = None,
-                     check: bool = True) -> torch.Tensor:
+                     check: bool = True, status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Membership bitmaps: int32-typed uint32 [W, ceil(n_docs/32)]."""
     lib = _lib.load()
     _query_common(f1, f2, f3)
@@ -271,7 +271,8 @@ def query_membership(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_sta
     nw = (n_docs + 31) // 32
     if out is None:
         out = torch.empty((W, nw), dtype=torch.int32, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
     rc = lib.memo_query_membership(_ptr(f1), _ptr(f2), _ptr(f3), f1.numel(), q_start, q_end, k,
                                    n_docs, _ptr(out), status.data_ptr(), 0, 0, _stream_ptr(dev))
     _lib.check(rc, "memo_query_membership")

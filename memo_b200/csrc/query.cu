@@ -17,7 +17,7 @@
 namespace memo {
 namespace {
 
-constexpr int QT_MIN = 8192;   // window positions per tile
+constexpr int QT_MIN = 2048;   // smallest tile (window positions): the bounds workspace is sized for it
 constexpr int QTHREADS = 256;
 
 // lo[t] = first row with f1 > s + t*QT              (t = 0..n_tiles-1)
@@ -68,16 +68,41 @@ query_conservation_kernel(const int32_t* __restrict__ f1, const uint32_t* __rest
         const long long nr0 = tn < n_tiles ? lo[tn] : 0, nr1 = tn < n_tiles ? hi[tn] : 0;
         for (int i = threadIdx.x; i < QT; i += TH) tile[i] = (uint32_t)n_docs;
         __syncthreads();
-        auto paint = [&](int32_t a1, uint32_t a2, int32_t ord) {
+        // Row r paints [cend, start).  If the row before it starts at the same position, has
+        // an order <= this one and ends no earlier, it covers the tail [its cend, start) with
+        // a value at least as small: this row then only paints up to that cend.  (Rows of one
+        // position come in ascending order with descending ends, so a position's rows paint
+        // every window position once instead of once per row.)
+        auto paint = [&](long long r, int32_t a1, uint32_t a2, int32_t ord) {
             const long long start = (long long)a1 - s;                    // > t0 by construction
             const long long cend = (long long)a2 - s - (k - 1);
             if (ord < 0 || ord > n_docs) { *status = 1; return; }
             const long long a = max(cend, t0);                            // clip to [0, W] and to the tile
-            const long long b = min(start, t1);
+            long long b = min(start, t1);
+            if (r > 0 && b > a) {
+                const int32_t p1 = f1[r - 1], p3 = f3[r - 1];
+                const uint32_t p2 = f2[r - 1];
+                if (p1 == a1 && p3 >= 0 && p3 <= ord && p2 >= a2) b = min(b, (long long)p2 - s - (k - 1));
+            }
             for (long long q = a; q < b; ++q) atomicMin(&tile[q - t0], (uint32_t)ord);
         };
-        if (have) paint(v1, v2, v3);
-        for (r += TH; r < r1; r += TH) paint(f1[r], f2[r], f3[r]);
+        if (have) paint(r, v1, v2, v3);
+        // four rows per thread in flight
+        for (r += TH; r < r1; r += 4 * TH) {
+            int32_t w1[4], w3[4];
+            uint32_t w2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long rj = r + j * TH;
+                const bool ok = rj < r1;
+                w1[j] = ok ? f1[rj] : 0;
+                w2[j] = ok ? f2[rj] : 0u;
+                w3[j] = ok ? f3[rj] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (r + j * TH < r1) paint(r + j * TH, w1[j], w2[j], w3[j]);
+        }
         __syncthreads();
         const int n = (int)(t1 - t0);
         if (sizeof(OutT) == 1 && n == QT) {
@@ -175,7 +200,10 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     if (W == 0) return MEMO_OK;
     MEMO_REQUIRE(out != nullptr, "out must not be NULL");
     MEMO_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
-    constexpr int QT = 8192, TH = QTHREADS;   // measured on B200: tile / CTA size hardly matter (2048..8192, 64..256)
+    // tiles of 8192 positions; dense indexes (many rows per position) get smaller tiles so
+    // that the work per tile stays small against the number of tiles per CTA
+    constexpr int TH = QTHREADS;
+    const int QT = (n_rows > W / 2) ? 2048 : 8192;
     const long long n_tiles = (W + QT - 1) / QT;
     const size_t half = align_up(sizeof(long long) * (size_t)(n_tiles + 1), 256);
     if (workspace == nullptr || workspace_bytes < 2 * half) {
@@ -187,14 +215,14 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     query_bounds_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(f1, n_rows, q_start, k, QT, n_tiles, lo, hi);
     MEMO_CUDA_TRY(cudaGetLastError());
     const int sms = device_sm_count();
-    long long grid = (long long)sms * 5;     // 32 KB of shared memory per CTA
+    long long grid = (long long)sms * (QT == 8192 ? 5 : 8);     // by shared memory / by threads
     if (grid > n_tiles) grid = n_tiles;
-    if (out_u16)
-        query_conservation_kernel<uint16_t, QT, TH><<<(unsigned)grid, TH, 0, stream>>>(
-            f1, f2, f3, lo, hi, q_start, W, k, n_docs, static_cast<uint16_t*>(out), status);
-    else
-        query_conservation_kernel<uint8_t, QT, TH><<<(unsigned)grid, TH, 0, stream>>>(
-            f1, f2, f3, lo, hi, q_start, W, k, n_docs, static_cast<uint8_t*>(out), status);
+#define MEMO_QLAUNCH(TT, QQ)                                                                \
+    query_conservation_kernel<TT, QQ, TH><<<(unsigned)grid, TH, 0, stream>>>(               \
+        f1, f2, f3, lo, hi, q_start, W, k, n_docs, static_cast<TT*>(out), status)
+    if (out_u16) { if (QT == 8192) MEMO_QLAUNCH(uint16_t, 8192); else MEMO_QLAUNCH(uint16_t, 2048); }
+    else         { if (QT == 8192) MEMO_QLAUNCH(uint8_t, 8192); else MEMO_QLAUNCH(uint8_t, 2048); }
+#undef MEMO_QLAUNCH
     MEMO_CUDA_TRY(cudaGetLastError());
     return MEMO_OK;
 }
