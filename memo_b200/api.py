@@ -262,7 +262,8 @@ def query_conservation(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_s
 
 def query_membership(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_start: int,
                      q_end: int, k: int, n_docs: int, out: Optional[torch.Tensor] = None,
-                     check: bool = True, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     check: bool = True, status: Optional[torch.Tensor] = None,
+                     workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Membership bitmaps: int32-typed uint32 [W, ceil(n_docs/32)]."""
     lib = _lib.load()
     _query_common(f1, f2, f3)
@@ -273,8 +274,12 @@ def query_membership(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_sta
         out = torch.empty((W, nw), dtype=torch.int32, device=dev)
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = lib.memo_query_workspace_bytes(W)
+    ws = workspace if workspace is not None and workspace.numel() >= need else \
+        torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     rc = lib.memo_query_membership(_ptr(f1), _ptr(f2), _ptr(f3), f1.numel(), q_start, q_end, k,
-                                   n_docs, _ptr(out), status.data_ptr(), 0, 0, _stream_ptr(dev))
+                                   n_docs, _ptr(out), status.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(dev))
     _lib.check(rc, "memo_query_membership")
     if check and int(status.item()) != 0:
         raise IndexError("index row genome id out of range for -n (the reference writes out of bounds)")

@@ -12,6 +12,8 @@
 // index order (f1 ascending), so that is one contiguous range found by binary
 // search (bounds kernel).  The tile lives in shared memory; painting uses
 // shared-memory atomics, the result is written once, coalesced.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace memo {
@@ -181,7 +183,9 @@ extern "C" {
 size_t memo_query_workspace_bytes(int64_t window_len) {
     if (window_len < 0) window_len = 0;
     const int64_t n_tiles = (window_len + memo::QT_MIN - 1) / memo::QT_MIN;
-    return memo::align_up(sizeof(long long) * (size_t)(n_tiles + 1), 256) * 2;
+    const size_t tiles = memo::align_up(sizeof(long long) * (size_t)(n_tiles + 1), 256) * 2;
+    const size_t planes = memo::query_planes_workspace_bytes();
+    return tiles > planes ? tiles : planes;
 }
 
 int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t* f3,
@@ -200,6 +204,11 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     if (W == 0) return MEMO_OK;
     MEMO_REQUIRE(out != nullptr, "out must not be NULL");
     MEMO_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+    // uint8 results (n_docs <= 255): bit-plane tiles, one stream per warp (query_planes.cu)
+    if (!out_u16 && q_end + k < (1ll << 31) - (1ll << 17) &&
+        ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3)) & 15) == 0)
+        return launch_query_planes(f1, f2, f3, n_rows, q_start, q_end, k, n_docs, static_cast<uint8_t*>(out),
+                                   status, workspace, workspace_bytes, stream);
     // tiles of 8192 positions; dense indexes (many rows per position) get smaller tiles so
     // that the work per tile stays small against the number of tiles per CTA
     constexpr int TH = QTHREADS;

@@ -1,0 +1,408 @@
+// k-mer conservation query for n_docs <= 255 on sm_100a: bit-plane tiles.
+//
+// Replaces the reference's src/memo_query.py memo_init :42-55, memo_query :57-63
+// and the argmax of print_res :70 (see query.cu for the definition):
+//
+//   conservation[p] = min{ f3 : clip(f2 - s - (k-1)) <= p < clip(f1 - s) }, else n_docs
+//
+// The reference paints a [W, N+1] byte matrix, k-1 byte stores per index row.  A
+// shared-memory atomic per painted cell is what bounds a direct transcription
+// (ATOMS retires ~2 lanes per clock per SM).  Here a tile of TP window positions
+// is kept as one BIT-PLANE per order value: plane o has bit p set iff some row
+// with f3 == o covers position p.  A row covers at most k-1 consecutive
+// positions, i.e. it ORs one or two 32-bit words (k <= 33) instead of painting
+// 30 cells.  When the tile's rows are in, one lane per 32-position word column
+// walks the planes in ascending order (first plane with the bit set = the
+// minimum), keeps the result as 8 binary digit planes and expands those into the
+// 32 output bytes of its positions: two 128-bit coalesced stores per lane.
+//
+// Every WARP is an independent stream (no __syncthreads, no bounds pass): it
+// takes runs of consecutive tiles from an atomic counter, finds the first row of
+// the run with one cooperative 32-ary search and from then on walks the rows
+// forward 64 at a time (coalesced, next batch in flight) -- the first row of the
+// next tile is seen while the current tile's halo rows go by.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace memo {
+namespace {
+
+constexpr int QP_WARPS = 4;          // warps per CTA
+constexpr int QP_WORDS = 1280;       // shared-memory words per warp (all planes of its tile)
+constexpr int QP_HEAVY = 2048;       // rows after which a tile is handed on in 32-position pieces
+constexpr int QP_QCAP = 1024;        // heavy tiles that can be handed on per launch
+constexpr size_t QP_WS_HEADER = 256; // workspace: next run | 128 bytes on: number of heavy tiles | their records
+
+struct HeavyTile;
+
+struct PlaneParams {
+    const int32_t* f1;
+    const uint32_t* f2;
+    const int32_t* f3;
+    long long n_rows, s, W;
+    int k, n_docs;
+    int NOP;                       // planes per tile: n_docs rounded up to a multiple of the group size
+    int WPT;                       // words per plane
+    int TP;                        // positions per tile = 32 WPT
+    int run;                       // tiles per run
+    long long n_tiles, n_runs;
+    uint8_t* out;
+    int32_t* status;
+    unsigned long long* counter;   // next run
+    unsigned int* n_heavy;         // heavy tiles handed on so far (its own 128-byte line)
+    HeavyTile* heavy;              // [QP_QCAP]
+};
+
+struct __align__(16) HeavyTile {   // a tile handed on in 32-position pieces (32 bytes, zero = not written yet)
+    unsigned long long desc;       // (window position + 1) << 16 | pieces; readers wait for it
+    unsigned int next;             // next piece to take (may run past the number of pieces)
+    unsigned int pad[5];
+};
+
+// first row with f1 > key (n if none): 32 probes per round
+__device__ __forceinline__ long long warp_upper_bound(const int32_t* __restrict__ f1, long long n,
+                                                      long long key, int lane) {
+    long long lo = 0, hi = n;                       // the answer lies in [lo, hi]
+    while (hi - lo > 32) {
+        const long long span = hi - lo;
+        // probe l at lo + span (l+1) / 32 - 1: ascending in l, first >= lo, last = hi - 1
+        const long long idx = lo + ((span * (lane + 1)) >> 5) - 1;
+        const unsigned b = __ballot_sync(FULL, (long long)f1[idx] > key);
+        if (b == 0u) return hi;                      // row hi - 1 is not past the key
+        const int j = __ffs(b) - 1;
+        hi = lo + ((span * (j + 1)) >> 5) - 1;
+        if (j > 0) lo = lo + ((span * j) >> 5);
+    }
+    const long long idx = lo + lane;
+    const unsigned b = __ballot_sync(FULL, idx >= hi || (long long)f1[idx] > key);
+    return b ? lo + (__ffs(b) - 1) : hi;
+}
+
+struct RowBatch {                  // 128 consecutive rows: rows 4 lane .. 4 lane + 3 of the batch
+    int32_t a1[4];
+    uint32_t a2[4];
+    uint32_t a3[4];
+};
+
+__device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) {
+    return *reinterpret_cast<const volatile unsigned int*>(p);
+}
+
+// B = binary digits of the result that can be non-zero (n_docs < 2^B); GS = planes per
+// unrolled group of the read-out (P.NOP is a multiple of it)
+template <int B, int GS>
+__global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const PlaneParams P) {
+    constexpr int GB = GS == 8 ? 3 : 2;              // digits fixed by the position inside a group
+    __shared__ __align__(16) uint32_t smem[QP_WARPS][QP_WORDS];
+    const int lane = threadIdx.x & 31;
+    uint32_t* const planes = smem[threadIdx.x >> 5];
+    const int WPT = P.WPT, n_docs = P.n_docs;
+    const int n_words = P.NOP * WPT;
+    const uint32_t km1 = (uint32_t)(P.k - 1);
+    const int halo = (P.k > 2 ? P.k : 2) - 2;        // rows starting up to tile end + halo can cover
+    const long long n_rows = P.n_rows;
+
+    // One tile: window positions [t0, t0 + tn), rows from r on (the first row with f1 > s + t0).
+    // Returns the row where the next tile starts (the first one past this tile), or -1 if the
+    // tile turned out heavy and was handed on as 32-position pieces (splittable only).
+    // All arithmetic is 32-bit relative to the tile base (the window ends below 2^31 - 2^17:
+    // launch_query_planes checks).  Rows are read 128 at a time from the 4-aligned row below r
+    // (one 128-bit load per array and lane; f1, f2, f3 are 16-byte aligned): the up to three
+    // rows before r have f1 <= base and drop out as "not in"; rows past the end of the index
+    // read as f1 = INT_MAX.
+    auto do_tile = [&](const long long t0, const int tn, const long long r, const bool splittable) -> long long {
+        const int base = (int)(P.s + t0);
+        const uint32_t bk = (uint32_t)base + km1;
+        const uint32_t lim_in = (uint32_t)(tn + halo);
+        const long long ra = r & ~3ll;
+        const int32_t* const pf1 = P.f1 + ra;
+        const uint32_t* const pf2 = P.f2 + ra;
+        const int32_t* const pf3 = P.f3 + ra;
+        const int n32 = (int)min(n_rows - ra, 0x40000000ll);
+        auto load = [&](RowBatch& bt, int i) {
+            const int idx = i + 4 * lane;
+            if (idx + 3 < n32) {
+                const int4 v1 = *reinterpret_cast<const int4*>(pf1 + idx);
+                const uint4 v2 = *reinterpret_cast<const uint4*>(pf2 + idx);
+                const int4 v3 = *reinterpret_cast<const int4*>(pf3 + idx);
+                bt.a1[0] = v1.x; bt.a1[1] = v1.y; bt.a1[2] = v1.z; bt.a1[3] = v1.w;
+                bt.a2[0] = v2.x; bt.a2[1] = v2.y; bt.a2[2] = v2.z; bt.a2[3] = v2.w;
+                bt.a3[0] = (uint32_t)v3.x; bt.a3[1] = (uint32_t)v3.y; bt.a3[2] = (uint32_t)v3.z; bt.a3[3] = (uint32_t)v3.w;
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const bool ok = idx + h < n32;
+                    bt.a1[h] = ok ? pf1[idx + h] : 0x7FFFFFFF;
+                    bt.a2[h] = ok ? pf2[idx + h] : 0u;
+                    bt.a3[h] = ok ? (uint32_t)pf3[idx + h] : 0u;
+                }
+            }
+        };
+        RowBatch cur, nxt;
+        load(cur, 0);
+        // ---- all planes := empty
+        for (int i = lane * 4; i < n_words; i += 128)
+            *reinterpret_cast<uint4*>(planes + i) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        // ---- rows with base < f1 <= base + tn + halo, in order
+        int i = 0, n_before = 0;                       // rows walked; rows not past the tile end
+        bool bad = false;
+        for (;;) {
+            load(nxt, i + 128);
+            int c = 0;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int x = cur.a1[h] - base;
+                const bool in = (uint32_t)(x - 1) < lim_in;          // 0 < x <= tn + halo
+                c += x <= tn ? 1 : 0;
+                // the row covers [a, b) of the tile: a = clip(f2 - base - (k-1)), b = clip(x)
+                uint32_t a = min(cur.a2[h] - bk, (uint32_t)tn);
+                if (cur.a2[h] < bk) a = 0u;
+                const uint32_t b = (uint32_t)min(x, tn);
+                const uint32_t ord = cur.a3[h];
+                bad = bad || (in && ord > (uint32_t)n_docs);
+                if (in && b > a && ord < (uint32_t)n_docs) {         // order n_docs == "not covered"
+                    uint32_t* const pl = planes + ord * WPT;
+                    const uint32_t w0 = a >> 5, w1 = (b - 1u) >> 5;
+                    const uint32_t m0 = 0xFFFFFFFFu << (a & 31u);
+                    const uint32_t m1 = 0xFFFFFFFFu >> (31u - ((b - 1u) & 31u));
+                    if (w0 == w1) {
+                        atomicOr(pl + w0, m0 & m1);
+                    } else {
+                        atomicOr(pl + w0, m0);
+                        for (uint32_t w = w0 + 1; w < w1; ++w) atomicOr(pl + w, 0xFFFFFFFFu);
+                        atomicOr(pl + w1, m1);
+                    }
+                }
+            }
+            n_before += __reduce_add_sync(FULL, c);
+            // rows are in f1 order: the batch's last row tells whether the tile's rows are through
+            if (__shfl_sync(FULL, cur.a1[3], 31) - base > (int)lim_in) break;
+            cur = nxt;
+            i += 128;
+            if (splittable && i == QP_HEAVY && tn > 32) {
+                // a heavy tile (a dense stretch of the index): hand it on in 32-position pieces
+                const unsigned n_sub = (unsigned)(tn + 31) >> 5;
+                unsigned slot = 0xFFFFFFFFu;
+                if (lane == 0) {
+                    slot = atomicAdd(P.n_heavy, 1u);
+                    if (slot < (unsigned)QP_QCAP) {
+                        *reinterpret_cast<volatile unsigned long long*>(&P.heavy[slot].desc) =
+                            (((unsigned long long)t0 + 1ull) << 16) | n_sub;
+                    }
+                }
+                slot = __shfl_sync(FULL, slot, 0);
+                if (slot < (unsigned)QP_QCAP) return -1;
+            }
+        }
+        if (bad) *P.status = 1;
+        __syncwarp();
+        // ---- one lane per 32-position word column: the first plane with the bit set is the
+        //      minimum; kept as B binary digit planes.  Few word columns (many planes): the
+        //      planes are split between the two half-warps and merged afterwards.
+        const int halves = WPT <= 16 ? 2 : 1;
+        const int lpi = 32 / halves;                       // word columns per sweep
+        const int half = halves == 2 ? lane >> 4 : 0;
+        const int g_cnt = P.NOP / GS / halves;             // plane groups per lane
+        for (int wc0 = 0; 32 * wc0 < tn; wc0 += lpi) {
+            const int wc = wc0 + (lane & (lpi - 1));
+            uint32_t seen = 0u, dg[B];
+#pragma unroll
+            for (int bb = 0; bb < B; ++bb) dg[bb] = 0u;
+            // (idle lanes of a short sweep read the last column)
+            const uint32_t* col = planes + min(wc, WPT - 1) + half * g_cnt * GS * WPT;
+            for (int g = half * g_cnt; g < (half + 1) * g_cnt; ++g, col += GS * WPT) {
+                const uint32_t before = seen;
+#pragma unroll
+                for (int o = 0; o < GS; ++o) {
+                    const uint32_t M = col[o * WPT];
+                    const uint32_t S = M & ~seen;          // positions whose minimum is GS g + o
+                    seen |= M;
+#pragma unroll
+                    for (int bb = 0; bb < GB && bb < B; ++bb)
+                        if (o & (1 << bb)) dg[bb] |= S;
+                }
+                const uint32_t U = seen & ~before;          // positions decided in this group
+#pragma unroll
+                for (int bb = GB; bb < B; ++bb) dg[bb] |= ((g >> (bb - GB)) & 1) ? U : 0u;
+            }
+            if (halves == 2) {                             // the upper planes count where no lower one does
+                const uint32_t seen_hi = __shfl_down_sync(FULL, seen, 16);
+#pragma unroll
+                for (int bb = 0; bb < B; ++bb) dg[bb] |= __shfl_down_sync(FULL, dg[bb], 16) & ~seen;
+                seen |= seen_hi;
+            }
+            if (half != 0 || 32 * wc >= tn) continue;
+            const uint32_t none = ~seen;                   // nothing covers: n_docs
+#pragma unroll
+            for (int bb = 0; bb < B; ++bb) dg[bb] |= ((n_docs >> bb) & 1) ? none : 0u;
+            // digit planes -> bytes: output word j holds positions 4j .. 4j+3
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int bb = 0; bb < B; ++bb) {
+                    const uint32_t nib = (dg[bb] >> (4 * j)) & 0xFu;
+                    acc += ((nib * 0x00204081u) & 0x01010101u) << bb;
+                }
+                w[j] = acc;
+            }
+            uint8_t* const o = P.out + t0 + 32 * wc;
+            if (32 * wc + 32 <= tn) {
+                reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+                const int n = tn - 32 * wc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (4 * j + q < n) o[4 * j + q] = (uint8_t)(w[j] >> (8 * q));
+            }
+        }
+        __syncwarp();
+        return ra + (n_before < n32 ? n_before : n32);
+    };
+
+    // takes one piece of a heavy tile, if there is one left: its window position.  Every warp
+    // walks the records in order and leaves a record for good once its pieces are gone, so a
+    // record sees at most one failed take per warp.
+    unsigned hv_cur = 0, hv_seen = 0;                // hv_seen: number of records, read one run ahead
+    auto take_piece = [&](bool fresh) -> long long {
+        long long t0 = -1;
+        if (lane == 0) {
+            for (;;) {
+                unsigned nh = fresh ? ld_volatile(P.n_heavy) : hv_seen;
+                if (nh > (unsigned)QP_QCAP) nh = QP_QCAP;
+                if (hv_cur >= nh) break;
+                HeavyTile* const hv = P.heavy + hv_cur;
+                // one 16-byte read of {desc, next}: a same-address atomic per warp and record
+                // would cost more than the pieces are worth
+                unsigned long long desc, nx;
+                do {
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(desc), "=l"(nx) : "l"(hv));
+                } while (desc == 0ull);
+                const unsigned n_sub = (unsigned)(desc & 0xFFFFull);
+                if ((unsigned)nx < n_sub) {
+                    const unsigned j = atomicAdd(&hv->next, 1u);
+                    if (j < n_sub) {
+                        t0 = (long long)(desc >> 16) - 1 + 32ll * j;
+                        break;
+                    }
+                }
+                ++hv_cur;
+            }
+        }
+        hv_cur = __shfl_sync(FULL, hv_cur, 0);
+        return __shfl_sync(FULL, t0, 0);
+    };
+
+    unsigned long long look = 0;
+    if (lane == 0) look = atomicAdd(P.counter, 1ull);
+    long long t_cur = 0, t_end = 0, r_run = 0;       // the tiles left of the warp's run
+    bool finishing = false;                          // no runs left: only pieces
+    for (;;) {
+        long long t0, r;
+        int tn;
+        const bool from_run = t_cur < t_end;
+        if (from_run) {
+            t0 = t_cur * P.TP;
+            tn = (int)min((long long)P.TP, P.W - t0);
+            r = r_run >= 0 ? r_run : warp_upper_bound(P.f1, n_rows, P.s + t0, lane);
+        } else {
+            // between runs: pieces of heavy tiles go first.  Whoever queued pieces comes by
+            // here afterwards, so none is left behind.
+            t0 = take_piece(finishing);
+            if (t0 >= 0) {
+                tn = (int)min(32ll, P.W - t0);
+                r = warp_upper_bound(P.f1, n_rows, P.s + t0, lane);
+            } else if (finishing) {
+                break;
+            } else {
+                const long long run = (long long)__shfl_sync(FULL, look, 0);
+                if (run >= P.n_runs) {
+                    finishing = true;
+                } else {
+                    if (lane == 0) {
+                        look = atomicAdd(P.counter, 1ull);              // one run ahead: hides the latency
+                        hv_seen = ld_volatile(P.n_heavy);
+                    }
+                    t_cur = run * P.run;
+                    t_end = min(t_cur + (long long)P.run, P.n_tiles);
+                    r_run = -1;
+                }
+                continue;
+            }
+        }
+        const long long r_next = do_tile(t0, tn, r, from_run);
+        if (from_run) {
+            r_run = r_next;
+            ++t_cur;
+        }
+    }
+}
+
+typedef void (*planes_kernel_t)(const PlaneParams);
+
+}  // namespace
+
+size_t query_planes_workspace_bytes() { return QP_WS_HEADER + sizeof(HeavyTile) * QP_QCAP; }
+
+int launch_query_planes(const int32_t* f1, const uint32_t* f2, const int32_t* f3, int64_t n_rows,
+                        int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs, uint8_t* out,
+                        int32_t* status, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    PlaneParams P;
+    P.f1 = f1; P.f2 = f2; P.f3 = f3;
+    P.n_rows = n_rows; P.s = q_start; P.W = q_end - q_start;
+    P.k = k; P.n_docs = n_docs;
+    const int gs = n_docs <= 16 ? 4 : 8;
+    P.NOP = (n_docs + gs - 1) / gs * gs;
+    if (QP_WORDS / P.NOP <= 16) P.NOP = (n_docs + 2 * gs - 1) / (2 * gs) * (2 * gs);   // halves of the planes
+    int wpt = QP_WORDS / P.NOP;
+    if (wpt >= 32) wpt = wpt / 32 * 32;             // whole warps of word columns
+    if (wpt > 128) wpt = 128;
+    P.WPT = wpt;
+    P.TP = 32 * wpt;
+    P.n_tiles = (P.W + P.TP - 1) / P.TP;
+    P.out = out; P.status = status;
+    const size_t need = query_planes_workspace_bytes();
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+        return MEMO_ERR_WORKSPACE;
+    }
+    P.counter = static_cast<unsigned long long*>(workspace);
+    P.n_heavy = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 128);
+    P.heavy = reinterpret_cast<HeavyTile*>(static_cast<char*>(workspace) + QP_WS_HEADER);
+    MEMO_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+    int bits = 1;
+    while ((1 << bits) <= n_docs) ++bits;            // n_docs < 2^bits
+    planes_kernel_t fn;
+    int slot;
+    if (bits <= 3) { fn = query_planes_kernel<3, 4>; slot = 0; }
+    else if (bits <= 4) { fn = query_planes_kernel<4, 4>; slot = 1; }
+    else if (n_docs <= 16) { fn = query_planes_kernel<5, 4>; slot = 2; }
+    else if (bits <= 6) { fn = query_planes_kernel<6, 8>; slot = 3; }
+    else if (bits <= 7) { fn = query_planes_kernel<7, 8>; slot = 4; }
+    else { fn = query_planes_kernel<8, 8>; slot = 5; }
+    static int per_sm[6] = {0, 0, 0, 0, 0, 0};
+    if (per_sm[slot] == 0) {
+        int n = 0;
+        MEMO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, QP_WARPS * 32, 0));
+        per_sm[slot] = n > 0 ? n : 1;
+    }
+    const long long warps = (long long)device_sm_count() * per_sm[slot] * QP_WARPS;
+    // runs of consecutive tiles share one row search; about 3 runs per warp keep the tail short
+    long long run = P.n_tiles / (warps * 3);
+    P.run = (int)(run < 1 ? 1 : run > 16 ? 16 : run);
+    P.n_runs = (P.n_tiles + P.run - 1) / P.run;
+    long long grid = (long long)device_sm_count() * per_sm[slot];
+    const long long enough = (P.n_runs + QP_WARPS - 1) / QP_WARPS;
+    if (grid > enough) grid = enough;
+    fn<<<(unsigned)grid, QP_WARPS * 32, 0, stream>>>(P);
+    MEMO_CUDA_TRY(cudaGetLastError());
+    return MEMO_OK;
+}
+
+}  // namespace memo

@@ -19,3 +19,4 @@ timeout -k 10 900 ncu --set full --clock-control none --import-source on -k "reg
    python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --cols 93 --rows 10000000 > gpurun_out/ncu_full_c93.log 2>&1; echo "ncu full c93 rc=$?"
 timeout -k 10 300 python bench.py --no-cpu --no-e2e --cols 93 --rows 10000000 > gpurun_out/bench_c93.json 2> gpurun_out/bench_c93.err; cat gpurun_out/bench_c93.json
 ls -la gpurun_out
+timeout -k 10 300 python bench.py --no-cpu --no-e2e --membership --cols 93 --rows 5000000 > gpurun_out/bench_memb.json 2> gpurun_out/bench_memb.err; cat gpurun_out/bench_memb.json

@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path (through the C ABI) against the oracle and the
 reference-generated golden fixtures.  Bit-exact: everything here is integer."""
+import os
+
 import numpy as np
 import pytest
 
@@ -31,6 +33,18 @@ def assert_index_equal(got, want, ctx=""):
 
 
 def gpu_query(s, e, c, qs, qe, k, n_docs, membership):
+    """Conservation queries with uint8 results run through BOTH device paths (bit-plane
+    stream kernel and tile kernel, normally chosen by index density) and must agree."""
+    if not membership and n_docs <= 255 and "MEMO_QUERY_PLANES" not in os.environ:
+        outs = []
+        for mode in ("1", "0"):
+            os.environ["MEMO_QUERY_PLANES"] = mode
+            try:
+                outs.append(gpu_query(s, e, c, qs, qe, k, n_docs, membership))
+            finally:
+                del os.environ["MEMO_QUERY_PLANES"]
+        assert np.array_equal(outs[0][0], outs[1][0]), "bit-plane and tile query kernels disagree"
+        return outs[0]
     api = _api()
     f1 = torch.from_numpy(s.astype(np.int32)).cuda()
     f2 = torch.from_numpy(e.astype(np.uint32).view(np.int32)).cuda()
@@ -242,6 +256,27 @@ def test_query_invariant_valid_ms():
     out = api.query_conservation(res.start[:res.n], res.end[:res.n], res.order[:res.n], 0, L, k, C + 1)
     want = 1 + (dap >= k).sum(dim=1)
     assert torch.equal(out.to(torch.int64), want)
+
+
+@pytest.mark.parametrize("density,n_docs", [(3.0, 12), (0.3, 200), (0.002, 300), (0.05, 95)])
+def test_query_arbitrary_rows(density, n_docs):
+    """Index rows that no index build would produce (any parquet can be queried):
+    random ends >= start, unordered orders and ends within a start position,
+    long empty stretches; conservation (uint8 / uint16) and membership."""
+    rng = np.random.default_rng(int(density * 1000) + n_docs)
+    span = 200000
+    n = max(3, int(span * density))
+    s = np.sort(rng.integers(1, span, size=n))
+    e = s + rng.integers(0, 80, size=n) * (rng.random(n) < 0.8) + rng.integers(0, 5000, size=n) * (rng.random(n) < 0.1)
+    for membership in (False, True):
+        c = rng.integers(0, n_docs if membership else n_docs + 1, size=n)
+        for qs, qe in ((0, span + 3000), (span // 3, span // 3 + 70001), (5, 1029), (span - 10, span + 5000)):
+            for k in (2, 31, 64):
+                want = mo.query(s, e, c, qs, qe, k, n_docs, membership)
+                got, _ = gpu_query(s, e, c, qs, qe, k, n_docs, membership)
+                if not membership:
+                    got = got.astype(np.int64) & 0xFFFF
+                assert np.array_equal(got, want), (membership, qs, qe, k)
 
 
 def test_query_order_out_of_range_raises():
