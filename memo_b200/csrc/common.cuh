@@ -39,11 +39,14 @@ int device_sm_count();
 size_t general_workspace_bytes(int64_t rows, int32_t n_cols, const memo_segment_t* segs,
                                int32_t n_seg, const memo_index_opts_t* opts);
 
-// query_planes.cu: conservation query with uint8 results (n_docs <= 255), windows ending
-// below 2^31 - 2^17
+// query_planes.cu: conservation query with uint8 results (n_docs <= 255) and membership
+// query (n_docs <= query_planes_max_membership_docs()); windows ending below 2^31 - 2^17,
+// f1 / f2 / f3 16-byte aligned
 size_t query_planes_workspace_bytes();
-int launch_query_planes(const int32_t* f1, const uint32_t* f2, const int32_t* f3, int64_t n_rows,
-                        int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs, uint8_t* out,
-                        int32_t* status, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int query_planes_max_membership_docs();
+int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
+                        int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs,
+                        void* out, int32_t* status, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 
 }  // namespace memo

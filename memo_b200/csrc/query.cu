@@ -206,9 +206,10 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     MEMO_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
     // uint8 results (n_docs <= 255): bit-plane tiles, one stream per warp (query_planes.cu)
     if (!out_u16 && q_end + k < (1ll << 31) - (1ll << 17) &&
+        !(getenv("MEMO_QUERY_PLANES") && atoi(getenv("MEMO_QUERY_PLANES")) == 0) &&
         ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3)) & 15) == 0)
-        return launch_query_planes(f1, f2, f3, n_rows, q_start, q_end, k, n_docs, static_cast<uint8_t*>(out),
-                                   status, workspace, workspace_bytes, stream);
+        return launch_query_planes(0, f1, f2, f3, n_rows, q_start, q_end, k, n_docs, out, status, workspace,
+                                   workspace_bytes, stream);
     // tiles of 8192 positions; dense indexes (many rows per position) get smaller tiles so
     // that the work per tile stays small against the number of tiles per CTA
     constexpr int TH = QTHREADS;
@@ -253,6 +254,14 @@ int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* 
     MEMO_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), stream));
     if (W == 0) return MEMO_OK;
     MEMO_REQUIRE(out_bits != nullptr, "out_bits must not be NULL");
+    // bit-plane tiles, one stream per warp (query_planes.cu)
+    if (n_docs <= query_planes_max_membership_docs() && q_end + k < (1ll << 31) - (1ll << 17) &&
+        workspace != nullptr && workspace_bytes >= query_planes_workspace_bytes() &&
+        ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3) |
+          reinterpret_cast<uintptr_t>(out_bits)) & 15) == 0 &&
+        !(getenv("MEMO_QUERY_PLANES") && atoi(getenv("MEMO_QUERY_PLANES")) == 0))
+        return launch_query_planes(1, f1, f2, f3, n_rows, q_start, q_end, k, n_docs, out_bits, status, workspace,
+                                   workspace_bytes, stream);
     const int TP = QM_WORDS / NW;
     const long long n_tiles = (W + TP - 1) / TP;
     const int sms = device_sm_count();

@@ -16,6 +16,11 @@
 // minimum), keeps the result as 8 binary digit planes and expands those into the
 // 32 output bytes of its positions: two 128-bit coalesced stores per lane.
 //
+// Membership (-m) uses the same planes (one per genome) and row walk; its result IS a
+// bitmap, transposed: one lane per word column transposes 32 planes x 32 positions in
+// registers, the words go through the (already consumed) plane storage and out as rows
+// of ceil(n_docs/32) words per position.
+//
 // Every WARP is an independent stream (no __syncthreads, no bounds pass): it
 // takes runs of consecutive tiles from an atomic counter, finds the first row of
 // the run with one cooperative 32-ary search and from then on walks the rows
@@ -30,6 +35,7 @@ namespace {
 
 constexpr int QP_WARPS = 4;          // warps per CTA
 constexpr int QP_WORDS = 1280;       // shared-memory words per warp (all planes of its tile)
+constexpr int QP_WORDS_M = 2560;     // ... membership (needs 32 more for the skewed read-out)
 constexpr int QP_HEAVY = 2048;       // rows after which a tile is handed on in 32-position pieces
 constexpr int QP_QCAP = 1024;        // heavy tiles that can be handed on per launch
 constexpr size_t QP_WS_HEADER = 256; // workspace: next run | 128 bytes on: number of heavy tiles | their records
@@ -47,7 +53,7 @@ struct PlaneParams {
     int TP;                        // positions per tile = 32 WPT
     int run;                       // tiles per run
     long long n_tiles, n_runs;
-    uint8_t* out;
+    void* out;                     // uint8 [W] | membership: uint32 [W, NOP / 32]
     int32_t* status;
     unsigned long long* counter;   // next run
     unsigned int* n_heavy;         // heavy tiles handed on so far (its own 128-byte line)
@@ -79,6 +85,21 @@ __device__ __forceinline__ long long warp_upper_bound(const int32_t* __restrict_
     return b ? lo + (__ffs(b) - 1) : hi;
 }
 
+// 32 x 32 bit matrix transpose in registers: afterwards bit o of a[i] = former bit i of a[o]
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= t << j;
+            a[k + j] ^= t;
+        }
+        m ^= m << (j >> 1);
+    }
+}
+
 struct RowBatch {                  // 128 consecutive rows: rows 4 lane .. 4 lane + 3 of the batch
     int32_t a1[4];
     uint32_t a2[4];
@@ -91,10 +112,10 @@ __device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) {
 
 // B = binary digits of the result that can be non-zero (n_docs < 2^B); GS = planes per
 // unrolled group of the read-out (P.NOP is a multiple of it)
-template <int B, int GS>
+template <int B, int GS, bool MEMB>
 __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const PlaneParams P) {
     constexpr int GB = GS == 8 ? 3 : 2;              // digits fixed by the position inside a group
-    __shared__ __align__(16) uint32_t smem[QP_WARPS][QP_WORDS];
+    __shared__ __align__(16) uint32_t smem[QP_WARPS][MEMB ? QP_WORDS_M + 32 : QP_WORDS];
     const int lane = threadIdx.x & 31;
     uint32_t* const planes = smem[threadIdx.x >> 5];
     const int WPT = P.WPT, n_docs = P.n_docs;
@@ -161,8 +182,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 if (cur.a2[h] < bk) a = 0u;
                 const uint32_t b = (uint32_t)min(x, tn);
                 const uint32_t ord = cur.a3[h];
-                bad = bad || (in && ord > (uint32_t)n_docs);
-                if (in && b > a && ord < (uint32_t)n_docs) {         // order n_docs == "not covered"
+                // (conservation: order n_docs is valid and means "not covered")
+                bad = bad || (in && (MEMB ? ord >= (uint32_t)n_docs : ord > (uint32_t)n_docs));
+                if (in && b > a && ord < (uint32_t)n_docs) {
                     uint32_t* const pl = planes + ord * WPT;
                     const uint32_t w0 = a >> 5, w1 = (b - 1u) >> 5;
                     const uint32_t m0 = 0xFFFFFFFFu << (a & 31u);
@@ -198,6 +220,34 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
         }
         if (bad) *P.status = 1;
         __syncwarp();
+        if (MEMB) {
+            // ---- planes -> rows of NW words per position.  One group of 32 genomes at a time,
+            //      last group first: lane wc transposes the 32 x 32 bits of its word column and
+            //      parks the 32 words in the group's own (now consumed) plane storage, skewed by
+            //      one word per column (conflict free; the skew spills into the storage of the
+            //      group above, which is done with); then the words go out in position order.
+            const int NW = P.NOP >> 5;
+            const uint32_t last_mask = (n_docs & 31) ? ((1u << (n_docs & 31)) - 1u) : 0xFFFFFFFFu;
+            uint32_t* const ob = static_cast<uint32_t*>(P.out) + t0 * NW;
+            const bool act = lane < WPT && 32 * lane < tn;
+            for (int g = NW - 1; g >= 0; --g) {
+                uint32_t* const reg = planes + 32 * g * WPT;
+                uint32_t A[32];
+#pragma unroll
+                for (int o = 0; o < 32; ++o) A[o] = act ? reg[o * WPT + lane] : 0u;
+                __syncwarp();
+                transpose32(A);
+                const uint32_t gm = g == NW - 1 ? last_mask : 0xFFFFFFFFu;
+                if (act) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) reg[lane * 33 + q] = ~A[q] & gm;
+                }
+                __syncwarp();
+                for (int u = lane; u < tn; u += 32) ob[(long long)u * NW + g] = reg[(u >> 5) * 33 + (u & 31)];
+                __syncwarp();
+            }
+            return ra + (n_before < n32 ? n_before : n32);
+        }
         // ---- one lane per 32-position word column: the first plane with the bit set is the
         //      minimum; kept as B binary digit planes.  Few word columns (many planes): the
         //      planes are split between the two half-warps and merged afterwards.
@@ -249,7 +299,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 }
                 w[j] = acc;
             }
-            uint8_t* const o = P.out + t0 + 32 * wc;
+            uint8_t* const o = static_cast<uint8_t*>(P.out) + t0 + 32 * wc;
             if (32 * wc + 32 <= tn) {
                 reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -350,19 +400,34 @@ typedef void (*planes_kernel_t)(const PlaneParams);
 
 size_t query_planes_workspace_bytes() { return QP_WS_HEADER + sizeof(HeavyTile) * QP_QCAP; }
 
-int launch_query_planes(const int32_t* f1, const uint32_t* f2, const int32_t* f3, int64_t n_rows,
-                        int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs, uint8_t* out,
-                        int32_t* status, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+// Largest n_docs the membership variant takes (one word column of all planes must fit)
+int query_planes_max_membership_docs() { return QP_WORDS_M; }
+
+int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
+                        int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs,
+                        void* out, int32_t* status, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
     PlaneParams P;
     P.f1 = f1; P.f2 = f2; P.f3 = f3;
     P.n_rows = n_rows; P.s = q_start; P.W = q_end - q_start;
     P.k = k; P.n_docs = n_docs;
-    const int gs = n_docs <= 16 ? 4 : 8;
-    P.NOP = (n_docs + gs - 1) / gs * gs;
-    if (QP_WORDS / P.NOP <= 16) P.NOP = (n_docs + 2 * gs - 1) / (2 * gs) * (2 * gs);   // halves of the planes
-    int wpt = QP_WORDS / P.NOP;
-    if (wpt >= 32) wpt = wpt / 32 * 32;             // whole warps of word columns
-    if (wpt > 128) wpt = 128;
+    int wpt;
+    if (membership) {
+        P.NOP = (n_docs + 31) / 32 * 32;                 // groups of 32 genomes = output words
+        wpt = QP_WORDS_M / P.NOP;
+        if (wpt > 32) wpt = 32;                          // one lane per word column
+        if (wpt < 1) {
+            set_error("n_docs = %d too large for the membership planes", n_docs);
+            return MEMO_ERR_UNSUPPORTED;
+        }
+    } else {
+        const int gs = n_docs <= 16 ? 4 : 8;
+        P.NOP = (n_docs + gs - 1) / gs * gs;
+        if (QP_WORDS / P.NOP <= 16) P.NOP = (n_docs + 2 * gs - 1) / (2 * gs) * (2 * gs);   // halves of the planes
+        wpt = QP_WORDS / P.NOP;
+        if (wpt >= 32) wpt = wpt / 32 * 32;             // whole warps of word columns
+        if (wpt > 128) wpt = 128;
+    }
     P.WPT = wpt;
     P.TP = 32 * wpt;
     P.n_tiles = (P.W + P.TP - 1) / P.TP;
@@ -380,13 +445,14 @@ int launch_query_planes(const int32_t* f1, const uint32_t* f2, const int32_t* f3
     while ((1 << bits) <= n_docs) ++bits;            // n_docs < 2^bits
     planes_kernel_t fn;
     int slot;
-    if (bits <= 3) { fn = query_planes_kernel<3, 4>; slot = 0; }
-    else if (bits <= 4) { fn = query_planes_kernel<4, 4>; slot = 1; }
-    else if (n_docs <= 16) { fn = query_planes_kernel<5, 4>; slot = 2; }
-    else if (bits <= 6) { fn = query_planes_kernel<6, 8>; slot = 3; }
-    else if (bits <= 7) { fn = query_planes_kernel<7, 8>; slot = 4; }
-    else { fn = query_planes_kernel<8, 8>; slot = 5; }
-    static int per_sm[6] = {0, 0, 0, 0, 0, 0};
+    if (membership) { fn = query_planes_kernel<1, 4, true>; slot = 6; }
+    else if (bits <= 3) { fn = query_planes_kernel<3, 4, false>; slot = 0; }
+    else if (bits <= 4) { fn = query_planes_kernel<4, 4, false>; slot = 1; }
+    else if (n_docs <= 16) { fn = query_planes_kernel<5, 4, false>; slot = 2; }
+    else if (bits <= 6) { fn = query_planes_kernel<6, 8, false>; slot = 3; }
+    else if (bits <= 7) { fn = query_planes_kernel<7, 8, false>; slot = 4; }
+    else { fn = query_planes_kernel<8, 8, false>; slot = 5; }
+    static int per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
     if (per_sm[slot] == 0) {
         int n = 0;
         MEMO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, QP_WARPS * 32, 0));

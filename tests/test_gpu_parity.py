@@ -33,9 +33,10 @@ def assert_index_equal(got, want, ctx=""):
 
 
 def gpu_query(s, e, c, qs, qe, k, n_docs, membership):
-    """Conservation queries with uint8 results run through BOTH device paths (bit-plane
-    stream kernel and tile kernel, normally chosen by index density) and must agree."""
-    if not membership and n_docs <= 255 and "MEMO_QUERY_PLANES" not in os.environ:
+    """Queries the bit-plane stream kernels take (uint8 conservation, membership) run
+    through BOTH device paths (MEMO_QUERY_PLANES=0 selects the tile kernels that serve
+    everything else) and must agree."""
+    if (membership or n_docs <= 255) and "MEMO_QUERY_PLANES" not in os.environ:
         outs = []
         for mode in ("1", "0"):
             os.environ["MEMO_QUERY_PLANES"] = mode
