@@ -36,8 +36,8 @@ namespace {
 constexpr int QP_WARPS = 4;          // warps per CTA
 constexpr int QP_WORDS = 1280;       // shared-memory words per warp (all planes of its tile)
 constexpr int QP_WORDS_M = 2560;     // ... membership (needs 32 more for the skewed read-out)
-constexpr int QP_HEAVY = 2048;       // rows after which a tile is handed on in 32-position pieces
-constexpr int QP_QCAP = 1024;        // heavy tiles that can be handed on per launch
+constexpr int QP_HEAVY = 2048;       // rows after which a tile is handed on in (up to 8) pieces
+constexpr int QP_QCAP = 256;         // heavy tiles that can be handed on per launch (the others are walked as they are)
 constexpr size_t QP_WS_HEADER = 256; // workspace: next run | 128 bytes on: number of heavy tiles | their records
 
 struct HeavyTile;
@@ -52,6 +52,7 @@ struct PlaneParams {
     int WPT;                       // words per plane
     int TP;                        // positions per tile = 32 WPT
     int run;                       // tiles per run
+    int heavy_rows;                // rows after which a tile is handed on in pieces
     long long n_tiles, n_runs;
     void* out;                     // uint8 [W] | membership: uint32 [W, NOP / 32]
     int32_t* status;
@@ -60,8 +61,10 @@ struct PlaneParams {
     HeavyTile* heavy;              // [QP_QCAP]
 };
 
-struct __align__(16) HeavyTile {   // a tile handed on in 32-position pieces (32 bytes, zero = not written yet)
-    unsigned long long desc;       // (window position + 1) << 16 | pieces; readers wait for it
+struct __align__(16) HeavyTile {   // a tile handed on in pieces (32 bytes, zero = not written yet)
+    // (window position + 1) << 28 | positions << 12 | words per piece << 4 | pieces (<= 8);
+    // readers wait for it to become non-zero
+    unsigned long long desc;
     unsigned int next;             // next piece to take (may run past the number of pieces)
     unsigned int pad[5];
 };
@@ -106,10 +109,6 @@ struct RowBatch {                  // 128 consecutive rows: rows 4 lane .. 4 lan
     uint32_t a3[4];
 };
 
-__device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) {
-    return *reinterpret_cast<const volatile unsigned int*>(p);
-}
-
 // B = binary digits of the result that can be non-zero (n_docs < 2^B); GS = planes per
 // unrolled group of the read-out (P.NOP is a multiple of it)
 template <int B, int GS, bool MEMB>
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
 
     // One tile: window positions [t0, t0 + tn), rows from r on (the first row with f1 > s + t0).
     // Returns the row where the next tile starts (the first one past this tile), or -1 if the
-    // tile turned out heavy and was handed on as 32-position pieces (splittable only).
+    // tile turned out heavy and was handed on in pieces (splittable, more than 32 positions).
     // All arithmetic is 32-bit relative to the tile base (the window ends below 2^31 - 2^17:
     // launch_query_planes checks).  Rows are read 128 at a time from the 4-aligned row below r
     // (one 128-bit load per array and lane; f1, f2, f3 are 16-byte aligned): the up to three
@@ -203,15 +202,19 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
             if (__shfl_sync(FULL, cur.a1[3], 31) - base > (int)lim_in) break;
             cur = nxt;
             i += 128;
-            if (splittable && i == QP_HEAVY && tn > 32) {
-                // a heavy tile (a dense stretch of the index): hand it on in 32-position pieces
-                const unsigned n_sub = (unsigned)(tn + 31) >> 5;
+            if (splittable && i == P.heavy_rows && tn > 32) {
+                // a heavy tile (a dense stretch of the index): hand it on as up to 8 pieces of
+                // whole 32-position words; a piece that is still heavy is split again
+                const unsigned words = (unsigned)(tn + 31) >> 5;
+                const unsigned piece = (words + 7u) >> 3;
+                const unsigned n_sub = (words + piece - 1u) / piece;
                 unsigned slot = 0xFFFFFFFFu;
                 if (lane == 0) {
                     slot = atomicAdd(P.n_heavy, 1u);
                     if (slot < (unsigned)QP_QCAP) {
                         *reinterpret_cast<volatile unsigned long long*>(&P.heavy[slot].desc) =
-                            (((unsigned long long)t0 + 1ull) << 16) | n_sub;
+                            (((unsigned long long)t0 + 1ull) << 28) | ((unsigned long long)tn << 12) |
+                            (unsigned long long)(piece << 4) | n_sub;
                     }
                 }
                 slot = __shfl_sync(FULL, slot, 0);
@@ -243,7 +246,11 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                     for (int q = 0; q < 32; ++q) reg[lane * 33 + q] = ~A[q] & gm;
                 }
                 __syncwarp();
-                for (int u = lane; u < tn; u += 32) ob[(long long)u * NW + g] = reg[(u >> 5) * 33 + (u & 31)];
+                {
+                    uint32_t* dst = ob + lane * NW + g;
+                    const uint32_t* src = reg + lane;
+                    for (int u = lane; u < tn; u += 32, dst += 32 * NW, src += 33) *dst = *src;
+                }
                 __syncwarp();
             }
             return ra + (n_before < n32 ? n_before : n32);
@@ -320,33 +327,42 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
     // walks the records in order and leaves a record for good once its pieces are gone, so a
     // record sees at most one failed take per warp.
     unsigned hv_cur = 0, hv_seen = 0;                // hv_seen: number of records, read one run ahead
-    auto take_piece = [&](bool fresh) -> long long {
-        long long t0 = -1;
-        if (lane == 0) {
-            for (;;) {
-                unsigned nh = fresh ? ld_volatile(P.n_heavy) : hv_seen;
-                if (nh > (unsigned)QP_QCAP) nh = QP_QCAP;
-                if (hv_cur >= nh) break;
-                HeavyTile* const hv = P.heavy + hv_cur;
-                // one 16-byte read of {desc, next}: a same-address atomic per warp and record
-                // would cost more than the pieces are worth
-                unsigned long long desc, nx;
+    auto ld_heavy = [&]() -> unsigned {
+        return *reinterpret_cast<const volatile unsigned int*>(P.n_heavy);
+    };
+    auto take_piece = [&](bool fresh, int& tn_out) -> long long {
+        unsigned nh = fresh ? ld_heavy() : __shfl_sync(FULL, hv_seen, 0);       // (read by lane 0)
+        if (nh > (unsigned)QP_QCAP) nh = QP_QCAP;
+        while (hv_cur < nh) {
+            // 32 records per look: one 16-byte read of {desc, next} each (a same-address atomic
+            // per warp and record would cost more than the pieces are worth)
+            const unsigned idx = hv_cur + lane;
+            unsigned long long desc = 0, nx = 0;
+            if (idx < nh) {
                 do {
-                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(desc), "=l"(nx) : "l"(hv));
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(desc), "=l"(nx) : "l"(P.heavy + idx));
                 } while (desc == 0ull);
-                const unsigned n_sub = (unsigned)(desc & 0xFFFFull);
-                if ((unsigned)nx < n_sub) {
-                    const unsigned j = atomicAdd(&hv->next, 1u);
-                    if (j < n_sub) {
-                        t0 = (long long)(desc >> 16) - 1 + 32ll * j;
-                        break;
-                    }
-                }
-                ++hv_cur;
             }
+            const unsigned live = __ballot_sync(FULL, idx < nh && (unsigned)nx < (unsigned)(desc & 0xFull));
+            if (live == 0u) {
+                hv_cur = min(hv_cur + 32u, nh);
+                continue;
+            }
+            const int src = __ffs(live) - 1;                 // the records before it are exhausted
+            unsigned j = 0;
+            if (lane == src) j = atomicAdd(&P.heavy[idx].next, 1u);
+            j = __shfl_sync(FULL, j, src);
+            desc = __shfl_sync(FULL, desc, src);
+            hv_cur += src;
+            if (j < (unsigned)(desc & 0xFull)) {
+                const int plen = 32 * (int)((desc >> 4) & 0xFFull);
+                const int total = (int)((desc >> 12) & 0xFFFFull);
+                tn_out = min(plen, total - plen * (int)j);
+                return (long long)(desc >> 28) - 1 + (long long)plen * j;
+            }
+            ++hv_cur;                                        // lost the last piece to another warp
         }
-        hv_cur = __shfl_sync(FULL, hv_cur, 0);
-        return __shfl_sync(FULL, t0, 0);
+        return -1;
     };
 
     unsigned long long look = 0;
@@ -364,9 +380,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
         } else {
             // between runs: pieces of heavy tiles go first.  Whoever queued pieces comes by
             // here afterwards, so none is left behind.
-            t0 = take_piece(finishing);
+            t0 = take_piece(finishing, tn);
             if (t0 >= 0) {
-                tn = (int)min(32ll, P.W - t0);
                 r = warp_upper_bound(P.f1, n_rows, P.s + t0, lane);
             } else if (finishing) {
                 break;
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 } else {
                     if (lane == 0) {
                         look = atomicAdd(P.counter, 1ull);              // one run ahead: hides the latency
-                        hv_seen = ld_volatile(P.n_heavy);
+                        hv_seen = ld_heavy();
                     }
                     t_cur = run * P.run;
                     t_end = min(t_cur + (long long)P.run, P.n_tiles);
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 continue;
             }
         }
-        const long long r_next = do_tile(t0, tn, r, from_run);
+        const long long r_next = do_tile(t0, tn, r, true);
         if (from_run) {
             r_run = r_next;
             ++t_cur;
@@ -432,6 +447,11 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     P.TP = 32 * wpt;
     P.n_tiles = (P.W + P.TP - 1) / P.TP;
     P.out = out; P.status = status;
+    // a tile is heavy when it has walked many times the average tile's rows
+    P.heavy_rows = QP_HEAVY;
+    if (P.n_tiles > 0 && 8 * (n_rows / P.n_tiles) > P.heavy_rows)
+        P.heavy_rows = (int)min(8 * (n_rows / P.n_tiles), (long long)(1 << 30)) / 128 * 128;
+    if (const char* e = getenv("MEMO_QUERY_HEAVY")) P.heavy_rows = atoi(e) / 128 * 128;   // tuning: 0 = never
     const size_t need = query_planes_workspace_bytes();
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("workspace too small: %zu < %zu", workspace_bytes, need);
