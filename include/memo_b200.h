@@ -156,7 +156,9 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
 
 /* Membership query (-m): out_bits is device uint32 [W, ceil(n_docs/32)], bit j
  * of a row = column j of the reference's matrix (memo_query.py:51,60-62,68):
- * bit 0 (pivot) set, bit j cleared iff a row with f3 == j covers the k-mer. */
+ * bit 0 (pivot) set, bit j cleared iff a row with f3 == j covers the k-mer.
+ * workspace: memo_query_workspace_bytes(W) bytes (without it the slower tile
+ * kernel runs). */
 int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* f3,
                           int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k,
                           int32_t n_docs, uint32_t* out_bits, int32_t* status,
