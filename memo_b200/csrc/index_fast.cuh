@@ -117,7 +117,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // at most half of the reserved rows are ever wasted).  All members are warp
 // uniform; every method must be called by the whole warp.
 struct StripOut {
-    unsigned long long w_cur = 0, w_end = 0;       // the warp's reserved scratch rows
+    uint32_t* w_ptr = nullptr;                     // next scratch row of the warp's chunk
+    uint32_t w_left = 0;                           // rows left in the chunk
+    bool w_ok = true;                              // the chunk lies inside the scratch area
+    unsigned long long w_end = 0;                  // scratch row index after the chunk
     unsigned long long blk_off = 0;                // open block of the strip
     uint32_t blk_cnt = 0, total = 0;               // rows in the open block / in the strip
     int nblk = 0, last_rec = -1;                   // blocks closed so far; pool index of the last one
@@ -126,7 +129,7 @@ struct StripOut {
     __device__ __forceinline__ void begin(long long strip_id) {
         strip = strip_id;
         nblk = 0;
-        blk_off = w_cur;
+        blk_off = w_end - w_left;
         blk_cnt = 0;
         total = 0;
     }
@@ -152,24 +155,30 @@ struct StripOut {
         }
         ++nblk;
     }
-    // `n` consecutive scratch rows for the strip's next index rows; returns the first
-    __device__ __forceinline__ unsigned long long reserve(const FastParams& P, uint32_t n, int lane) {
-        if (n > w_end - w_cur) {                   // next chunk: the strip continues in a new block
-            close_block(P, lane);
-            const unsigned long long want = n > P.chunk ? n : P.chunk;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.cursor, want);
-            base = __shfl_sync(FULL, base, 0);
-            w_cur = base;
-            w_end = base + want;
-            blk_off = base;
-            blk_cnt = 0;
-        }
-        const unsigned long long at = w_cur;
-        w_cur += n;
+    // next chunk: the strip continues in a new block
+    __device__ __forceinline__ void new_chunk(const FastParams& P, uint32_t n, int lane) {
+        close_block(P, lane);
+        const unsigned long long want = n > P.chunk ? n : P.chunk;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.cursor, want);
+        base = __shfl_sync(FULL, base, 0);
+        w_ptr = P.scr + base * 3;
+        w_left = (uint32_t)want;
+        w_end = base + want;
+        w_ok = w_end <= (unsigned long long)P.scr_cap;    // (a chunk past the end stores nothing:
+        blk_off = base;                                   //  its rows are counted, the caller retries)
+        blk_cnt = 0;
+    }
+    // `n` consecutive scratch rows ({start, end, order} records) for the strip's next index
+    // rows; returns the first, or nullptr if the scratch area is exhausted
+    __device__ __forceinline__ uint32_t* reserve(const FastParams& P, uint32_t n, int lane) {
+        if (n > w_left) new_chunk(P, n, lane);
+        uint32_t* const at = w_ptr;
+        w_ptr += 3 * n;
+        w_left -= n;
         blk_cnt += n;
         total += n;
-        return at;
+        return w_ok ? at : nullptr;
     }
     __device__ __forceinline__ void end(const FastParams& P, int lane) {
         close_block(P, lane);

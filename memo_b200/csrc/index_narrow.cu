@@ -226,17 +226,16 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         }
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         if (total) {
-            const unsigned long long base = so.reserve(P, total, lane);
-            unsigned long long gi = base + (incl - cnt);
-            unsigned mm = (gi + cnt <= (unsigned long long)P.scr_cap) ? m : 0u;
+            uint32_t* dst = so.reserve(P, total, lane);
+            unsigned mm = dst ? m : 0u;
+            dst += (incl - cnt) * 3u;
             while (mm) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
-                uint32_t* dst = P.scr + gi * 3;
                 dst[0] = p;
                 dst[1] = q[2 + c];
                 dst[2] = (uint32_t)(c + 1);
-                ++gi;
+                dst += 3;
             }
         }
         __syncwarp();

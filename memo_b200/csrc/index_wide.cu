@@ -163,9 +163,8 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
             total += __popc(b[k]);
         }
         if (total == 0) return;
-        const unsigned long long at = so.reserve(P, total, lane);
-        if (at + total <= (unsigned long long)P.scr_cap) {
-            uint32_t* const dst0 = P.scr + at * 3;             // warp uniform
+        uint32_t* const dst0 = so.reserve(P, total, lane);             // warp uniform
+        if (dst0 != nullptr) {
             if (ORDER) {
 #pragma unroll
                 for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
@@ -245,17 +244,17 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                         const uint32_t y = x + __shfl_sync(FULL, myd, src);
                         uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
                         if (lane == 0) up = 0xFFFFFFFFu;
-                        uint32_t nA[KPL];
+                        // in place, last slot first: slot kk needs the old value of slot kk - 1
 #pragma unroll
-                        for (int kk = 0; kk < KPL; ++kk) {
+                        for (int kk = KPL - 1; kk >= 0; --kk) {
                             const uint32_t before = kk == 0 ? up : A[kk - 1];
-                            const bool inr = A[kk] >= x && A[kk] <= y;
-                            nA[kk] = inr ? min(before, y) : A[kk];
-                            em[kk] = inr && nA[kk] > A[kk] && A[kk] >= pos && ibase + kk < C;
-                            endv[kk] = A[kk];
+                            const uint32_t old = A[kk];
+                            const bool inr = old >= x && old <= y;
+                            const uint32_t nw = inr ? min(before, y) : old;
+                            em[kk] = nw > old && old >= pos && ibase + kk < C;
+                            endv[kk] = old;
+                            A[kk] = nw;
                         }
-#pragma unroll
-                        for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
                     } else {
                         uint32_t Aold[KPL];
 #pragma unroll
@@ -279,14 +278,11 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                                 const uint32_t y = x + __shfl_sync(FULL, myd, src);
                                 uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
                                 if (lane == 0) up = 0xFFFFFFFFu;
-                                uint32_t nA[KPL];
 #pragma unroll
-                                for (int kk = 0; kk < KPL; ++kk) {
+                                for (int kk = KPL - 1; kk >= 0; --kk) {
                                     const uint32_t before = kk == 0 ? up : A[kk - 1];
-                                    nA[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
+                                    A[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
                                 }
-#pragma unroll
-                                for (int kk = 0; kk < KPL; ++kk) A[kk] = nA[kk];
                             } while (m);
                         }
 #pragma unroll

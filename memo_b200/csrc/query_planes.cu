@@ -449,8 +449,8 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     P.out = out; P.status = status;
     // a tile is heavy when it has walked many times the average tile's rows
     P.heavy_rows = QP_HEAVY;
-    if (P.n_tiles > 0 && 8 * (n_rows / P.n_tiles) > P.heavy_rows)
-        P.heavy_rows = (int)min(8 * (n_rows / P.n_tiles), (long long)(1 << 30)) / 128 * 128;
+    if (P.n_tiles > 0 && 3 * (n_rows / P.n_tiles) > P.heavy_rows)
+        P.heavy_rows = (int)min(3 * (n_rows / P.n_tiles), (long long)(1 << 30)) / 128 * 128;
     if (const char* e = getenv("MEMO_QUERY_HEAVY")) P.heavy_rows = atoi(e) / 128 * 128;   // tuning: 0 = never
     const size_t need = query_planes_workspace_bytes();
     if (workspace == nullptr || workspace_bytes < need) {
