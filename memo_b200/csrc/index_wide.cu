@@ -223,14 +223,15 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                 if (ORDER) {
                     // cells whose MEM end moved up (a decrease makes the input irregular:
                     // flagged through irr_acc, skipped here)
-                    unsigned bk[KPL], ball = 0;
-                    int nchg = 0;
+                    bool ch[KPL];
+                    uint32_t cnt = 0;
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) {
-                        bk[k] = __ballot_sync(FULL, (int)(k == KPL - 1 ? (dk[k] & vm[k]) : dk[k]) > 0);
-                        ball |= bk[k];
-                        nchg += __popc(bk[k]);
+                        ch[k] = (int)(k == KPL - 1 ? (dk[k] & vm[k]) : dk[k]) > 0;
+                        cnt += ch[k] ? 1u : 0u;
                     }
+                    const unsigned ball = __ballot_sync(FULL, cnt != 0u);
+                    const uint32_t nchg = __reduce_add_sync(FULL, cnt);
                     if (nchg == 1) {
                         // the common case, one cell x -> y: the positions holding x <= A <= y
                         // shift down by one, y lands on the first of them, and exactly those
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                         uint32_t myx = prev[0], myd = dk[0];
 #pragma unroll
                         for (int k = 1; k < KPL; ++k)
-                            if (bk[k]) { myx = prev[k]; myd = dk[k]; }          // warp uniform
+                            if (ch[k]) { myx = prev[k]; myd = dk[k]; }
                         const int src = __ffs(ball) - 1;
                         const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
                         const uint32_t y = x + __shfl_sync(FULL, myd, src);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
                         // one cell per lane and round
                         unsigned todo = 0;
 #pragma unroll
-                        for (int k = 0; k < KPL; ++k) todo |= ((bk[k] >> lane) & 1u) << k;
+                        for (int k = 0; k < KPL; ++k) todo |= (ch[k] ? 1u : 0u) << k;
                         unsigned m;
                         while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
                             uint32_t myx = 0, myd = 0;
