@@ -307,3 +307,26 @@ def query(f1, f2, f3, q_start: int, q_end: int, k: int, n_docs: int, membership:
     torch.cuda.current_stream(dev).synchronize()
     host = raw_bytes.view(np.uint16 if out.dtype == torch.int16 else np.uint8)
     return host if raw else host.astype(np.int64)
+
+
+def query_sweep(f1, f2, f3, q_start: int, q_end: int, ks: Sequence[int], n_docs: int, membership: bool,
+                device=None, trusted: bool = False) -> dict:
+    """The same window queried for several k (BASELINE configs[4]: k = 15 .. 101): the index
+    rows go to the device once, every k is one query launch over them.  Returns {k: result}
+    with the results of `query` (conservation: uint8/uint16 numpy vectors; membership: uint8
+    [W, n_docs] matrices)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if q_end < q_start:
+        raise ValueError("negative dimensions are not allowed")
+    t1, t2, t3 = _rows_to_device(f1, f2, f3, dev, trusted)
+    W = q_end - q_start
+    ws = torch.empty(max(api._lib.load().memo_query_workspace_bytes(W), 1), dtype=torch.uint8, device=dev)
+    res = {}
+    for k in ks:
+        if membership:
+            bits = api.query_membership(t1, t2, t3, q_start, q_end, k, n_docs, workspace=ws)
+            res[k] = api.unpack_membership(bits.cpu().numpy(), n_docs)
+        else:
+            out = api.query_conservation(t1, t2, t3, q_start, q_end, k, n_docs, workspace=ws).cpu().numpy()
+            res[k] = out.view(np.uint16) if out.dtype == np.int16 else out
+    return res

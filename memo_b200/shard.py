@@ -213,3 +213,16 @@ def build_index_sharded(dap: torch.Tensor, plan: ShardPlan, n_cols: int, order: 
     n_local = torch.tensor([n], dtype=torch.int64, device=dev)
     counts, offset = ordered_offsets(n_local, group)
     return rows, counts, offset
+
+
+def query_rows_for_range(f1, lo: int, hi: int, k_max: int):
+    """Index rows a rank needs to answer queries with k <= k_max over window positions
+    [lo, hi) of a record: only rows with lo < f1 <= hi + k_max - 1 can cover them (f2 >= f1;
+    src/memo_query.py:25-27,46-49), i.e. its own rows plus a right halo of k_max - 1 positions
+    (SURVEY 8e).  f1: the record's row starts in index order (torch tensor or numpy array).
+    Returns the half-open row range (first, last); no collective is involved."""
+    import numpy as _np
+    a = f1.cpu().numpy() if isinstance(f1, torch.Tensor) else _np.asarray(f1)
+    first = int(_np.searchsorted(a, lo, side="right"))
+    last = int(_np.searchsorted(a, hi + max(k_max, 1) - 1, side="right"))
+    return first, last

@@ -280,6 +280,33 @@ def test_query_arbitrary_rows(density, n_docs):
                 assert np.array_equal(got, want), (membership, qs, qe, k)
 
 
+@pytest.mark.parametrize("C,membership", [(9, False), (40, False), (93, True)])
+def test_query_position_shards_and_k_sweep(C, membership):
+    """SURVEY 8e / BASELINE configs[4]: window positions split into ranges, every range
+    answered from its own rows plus a right halo of k_max - 1 positions, concatenated in
+    range order == the whole-window result, for a sweep of k."""
+    from memo_b200 import host, shard
+    L = 50000
+    vals = mo.synth_dap(L, C, seed=3 * C + 1, dense=True)
+    _, s, e, c = mo.index_build(vals, [("chrK", L)], not membership)
+    n_docs = C + 1
+    ks = (15, 31, 64, 101)
+    whole = host.query_sweep(s, e, c, 0, L, ks, n_docs, membership)
+    for k in ks:
+        want = mo.query(s, e, c, 0, L, k, n_docs, membership)
+        assert np.array_equal(whole[k].astype(np.int64), want), k
+    for world in (2, 3, 8):
+        parts = {k: [] for k in ks}
+        for rank in range(world):
+            lo, hi = shard.shard_range(L, world, rank)
+            a, b = shard.query_rows_for_range(s, lo, hi, max(ks))
+            got = host.query_sweep(s[a:b], e[a:b], c[a:b], lo, hi, ks, n_docs, membership)
+            for k in ks:
+                parts[k].append(got[k])
+        for k in ks:
+            assert np.array_equal(np.concatenate(parts[k]), whole[k]), (world, k)
+
+
 def test_query_order_out_of_range_raises():
     s = np.array([5, 9]); e = np.array([9, 12]); c = np.array([1, 7])
     with pytest.raises(IndexError):
