@@ -5,6 +5,10 @@ Same argv (src/dap_to_bed.py:139-149), same validation (:151-171), BED payload
 on stdout and nothing else (index.sh:93,102 redirect stdout into the .bed).
 
     python -m memo_b200.dap_to_bed --mem [--order] --overlap --fai P.fai --dap dap.txt > out.bed
+
+Extension (not in the reference): `--lengths G2.lengths G3.lengths ...` instead of
+`--dap` reads the per-genome MONI outputs directly (genome_list.txt order minus the
+pivot) and skips index.sh:79-83's vertical files, `paste | nl` and the text re-parse.
 """
 import argparse
 import os
@@ -15,7 +19,9 @@ def parse_arguments(argv=None):
     ap = argparse.ArgumentParser(description="Takes in .fai and full document array profile and "
                                  "converts to bed-style MEM intervals to stdout (B200 device path).")
     ap.add_argument("--fai", dest="fai_path", required=True, help="path to fai file")
-    ap.add_argument("--dap", dest="dap_path", required=True, help="path to full document profile")
+    ap.add_argument("--dap", dest="dap_path", default=None, help="path to full document profile")
+    ap.add_argument("--lengths", dest="lengths_paths", nargs="+", default=None,
+                    help="extension: per-genome MONI .lengths files instead of --dap")
     ap.add_argument("--ms", dest="print_ms", action="store_true", default=False,
                     help="Extract matching statistics (either MSs or MEMs, not both).")
     ap.add_argument("--mem", dest="print_mems", action="store_true", default=False,
@@ -30,8 +36,15 @@ def parse_arguments(argv=None):
 def check_args(args):
     if not os.path.isfile(args.fai_path):
         raise Exception("The fai file does not exist.")
-    if not os.path.isfile(args.dap_path):
-        raise Exception("The dap file does not exist.")
+    if args.lengths_paths is None:
+        if args.dap_path is None or not os.path.isfile(args.dap_path):
+            raise Exception("The dap file does not exist.")
+    else:
+        if args.dap_path is not None:
+            raise Exception("Error: Either --dap or --lengths, not both.")
+        for p in args.lengths_paths:
+            if not os.path.isfile(p):
+                raise Exception("The lengths file %s does not exist." % p)
     if not args.fai_path.endswith(".fai"):
         raise Exception("The fai file has the incorrect file extension.")
     if (args.print_ms + args.print_mems) != 1:
@@ -48,7 +61,10 @@ def main(args, sink=None):
     if not args.print_overlaps:
         raise NotImplementedError("only `--mem --overlap` (what `memo index` runs) is on the device path")
     records = api.parse_fai(args.fai_path)
-    pos0, dap = io.read_dap_text(args.dap_path)
+    if args.lengths_paths is not None:
+        pos0, dap = 0, io.read_lengths_columns(args.lengths_paths)
+    else:
+        pos0, dap = io.read_dap_text(args.dap_path)
     if dap.shape[0] == 0:
         raise KeyError(None)          # reference: fai_dict[None] after an empty DAP
     rec, start, end, col = host.build_index(dap, records, args.sort_lcps, pos_first=pos0)

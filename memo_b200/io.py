@@ -48,6 +48,42 @@ def read_dap_text(path) -> Tuple[int, np.ndarray]:
     return int(pos[0]), out
 
 
+def read_lengths_columns(paths: Sequence[str], threads: int = 8) -> np.ndarray:
+    """Per-genome MONI `*.lengths` (or the `*.lengths.vert` index.sh:79 makes of them) ->
+    int32 [L, C] DAP matrix, one column per file in the order given (genome_list.txt
+    order minus the pivot).  Replaces index.sh:79-83 (`grep -v '^>' | tr ' ' '\n'`,
+    `paste | nl`) and the text re-parse of dap.txt (src/dap_to_bed.py:87): header lines
+    start with '>', every other line holds whitespace-separated lengths; row i of the
+    result is pivot position i of the concatenated records."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(path):
+        with open(path, "rb") as fh:
+            data = fh.read()
+        if b">" in data:
+            data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b">"))
+        try:
+            col = np.array(data.split(), dtype=np.int64)
+        except ValueError as exc:                                # int() in the reference
+            raise ValueError(f"invalid literal for int() in {path}") from exc
+        if col.size and (col.min() < 0 or col.max() > 2**31 - 1):
+            raise MemoError("DAP lengths must be in [0, 2^31)")
+        return col.astype(np.int32)
+
+    if not paths:
+        raise MemoError("at least one .lengths file is needed")
+    with ThreadPoolExecutor(max(1, min(threads, len(paths)))) as ex:
+        cols = list(ex.map(one, paths))
+    L = cols[0].size
+    for path, col in zip(paths, cols):
+        if col.size != L:
+            raise MemoError(f"{path}: {col.size} lengths, expected {L} (one per pivot position)")
+    out = np.empty((L, len(cols)), dtype=np.int32)
+    for j, col in enumerate(cols):
+        out[:, j] = col
+    return out
+
+
 def index_table(records: Sequence[Tuple[str, int]], rec_idx, start, end, order) -> pa.Table:
     """Arrow table with the index schema (f0 string, f1..f3 int64), f0
     dictionary-free so that it equals what parquet_compress_bed.py reads back."""

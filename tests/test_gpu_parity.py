@@ -383,6 +383,15 @@ def test_cli_round_trip_example(example_golden, tmp_path, capsysbinary):
         with open(bed, "wb") as fh:
             dap_to_bed.main(args, sink=fh)
         assert bed.read_text() == g[bed_key]
+        # extension: the per-genome MONI .lengths files instead of dap.txt
+        from test_host_logic import _write_lengths
+        lens = _write_lengths(tmp_path, g["vals"])
+        args = dap_to_bed.parse_arguments(["--mem", "--overlap", "--fai", str(fai), "--lengths"] + lens +
+                                          (["--order"] if order else []))
+        dap_to_bed.check_args(args)
+        with open(tmp_path / f"{tag}_lengths.bed", "wb") as fh:
+            dap_to_bed.main(args, sink=fh)
+        assert (tmp_path / f"{tag}_lengths.bed").read_text() == g[bed_key]
         pq_path = tmp_path / f"{tag}.parquet"
         parquet_compress_bed.main(parquet_compress_bed.parse_arguments(["-f", str(bed), "-o", str(pq_path)]))
         capsysbinary.readouterr()

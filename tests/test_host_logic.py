@@ -75,6 +75,43 @@ def test_dap_text_ingest_and_bed_writer(example_golden, tmp_path):
         io.read_dap_text(str(bad))
 
 
+def _write_lengths(tmp_path, vals, per_line=(7, 1, 3)):
+    """MONI-style .lengths files for the columns of `vals`: a '>' header per record and
+    whitespace-separated lengths, several per line (what index.sh:79 flattens)."""
+    paths = []
+    for j in range(vals.shape[1]):
+        n = per_line[j % len(per_line)]
+        col = vals[:, j].tolist()
+        lines = [">pivot_record"]
+        for i in range(0, len(col), n):
+            lines.append(" ".join(str(v) for v in col[i:i + n]))
+            if i == 2 * n:
+                lines.append(">another_record")
+        p = tmp_path / f"g{j}.w_rc.lengths"
+        p.write_text("\n".join(lines) + "\n")
+        paths.append(str(p))
+    return paths
+
+
+def test_lengths_ingest_equals_dap_text(example_golden, tmp_path):
+    # SURVEY 8f rank 1: the per-genome MONI outputs read directly == paste | nl | re-parse
+    from memo_b200 import io
+    vals = example_golden["vals"]
+    paths = _write_lengths(tmp_path, vals)
+    assert np.array_equal(io.read_lengths_columns(paths), vals)
+    vert = tmp_path / "g0.vert"
+    vert.write_text("\n".join(str(v) for v in vals[:, 0]) + "\n")       # index.sh:79's vertical file
+    assert np.array_equal(io.read_lengths_columns([str(vert)])[:, 0], vals[:, 0])
+    short = tmp_path / "short.lengths"
+    short.write_text("1 2 3\n")
+    with pytest.raises(Exception, match="expected"):
+        io.read_lengths_columns([paths[0], str(short)])
+    bad = tmp_path / "bad.lengths"
+    bad.write_text("1 x 3\n")
+    with pytest.raises(ValueError):
+        io.read_lengths_columns([str(bad)])
+
+
 def test_parquet_compress_bed_cli(example_golden, tmp_path):
     bed = tmp_path / "x.bed"
     bed.write_text(example_golden["cons_bed"])
