@@ -482,6 +482,7 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     // runs of consecutive tiles share one row search; about 3 runs per warp keep the tail short
     long long run = P.n_tiles / (warps * 3);
     P.run = (int)(run < 1 ? 1 : run > 16 ? 16 : run);
+    if (const char* e = getenv("MEMO_QUERY_RUN")) P.run = atoi(e) > 0 ? atoi(e) : P.run;     // tuning
     P.n_runs = (P.n_tiles + P.run - 1) / P.run;
     long long grid = (long long)device_sm_count() * per_sm[slot];
     const long long enough = (P.n_runs + QP_WARPS - 1) / QP_WARPS;
