@@ -271,7 +271,9 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     // measured on B200: 2 x 8 warps per SM for tiles, 4 x 6 warps for strips
     plan->warps = (opts && opts->warps_per_cta > 0) ? opts->warps_per_cta : (plan->narrow ? 8 : 6);
     MEMO_REQUIRE(plan->warps >= 1 && plan->warps <= 8, "warps_per_cta must be 1..8");
-    plan->stages = (opts && opts->stages > 0) ? opts->stages : 2;
+    // measured on B200: tiles double-buffered per warp; strips in ONE large stage per warp (the
+    // other warps of the SM cover the copy: bigger chunks, fewer producer steps)
+    plan->stages = (opts && opts->stages > 0) ? opts->stages : (plan->narrow ? 2 : 1);
     MEMO_REQUIRE(plan->stages <= MAX_STAGES, "stages must be <= %d", MAX_STAGES);
     plan->ctas_per_sm = (opts && opts->ctas_per_sm > 0) ? opts->ctas_per_sm : 0;
     const long long row_bytes = (long long)ld * 4;
@@ -310,8 +312,12 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
         extra = 0;
     } else {
-        // strips of R rows stream through the ring in chunks of T rows (~3.75 KB)
-        T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : 3840 / row_bytes;
+        // strips of R rows stream through the ring in chunks of T rows: as many as keep four
+        // CTAs of `warps` warps on an SM (~9 KB per warp)
+        const long long per_warp = (227 * 1024 / 4 - 1024) / plan->warps - 8 * MAX_STAGES -
+                                   (long long)sizeof(TileDesc) * MAX_STAGES - 128;
+        T = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile
+                                              : (per_warp / plan->stages - 128 - 32 - 128 * plan->kpl) / row_bytes;
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
         if (T * row_bytes + 160 + 128 * plan->kpl > budget) T = (budget - 160 - 128 * plan->kpl) / row_bytes;
         if (T < 1) T = 1;
