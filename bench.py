@@ -173,12 +173,22 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
+    memb = getattr(args, "membership", False)
+    if args.cols == 9 and args.rows == 100_000_000 and not memb:
+        tag = "BASELINE configs[1]"
+    elif memb:
+        tag = "BASELINE configs[2]-shaped: membership index (-m) and per-genome presence bitmaps"
+    elif args.cols == 93:
+        tag = "BASELINE configs[3]-shaped shard: 94 genomes"
+    else:
+        tag = "non-default shape"
+    what = "membership index build + membership" if memb else "conservation index build +"
     return {"workload": f"synthetic HPRC-shaped DAP, {args.cols + 1} genomes x {args.rows} bp pivot "
-                        f"per GPU (BASELINE configs[1]), conservation index build + k={args.k} "
+                        f"per GPU ({tag}), {what} k={args.k} "
                         "window query over the whole shard",
             "genomes": args.cols + 1, "pivot_bp_per_gpu": args.rows, "k": args.k,
             "partition": f"position ranges x{n_gpus}, 1-row left halo, {KH}-row right halo",
-            "l2": "inputs (3.6 GB DAP per GPU) are larger than L2; no flush needed",
+            "l2": f"inputs ({args.rows * args.cols * 4 / 1e9:.2f} GB DAP per GPU) are larger than L2; no flush needed",
             "seed": SEED}
 
 
