@@ -33,6 +33,8 @@
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in
 // result[MEMO_RES_IRREGULAR].
+#include <stdlib.h>
+
 #include <vector>
 
 #include "index_fast.cuh"
@@ -234,6 +236,75 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
                 out_end[d] = v[j][1];
                 out_order[d] = (int32_t)v[j][2];
             }
+        }
+    }
+}
+
+// Variant: one warp per unit.  A unit's scratch rows (12-byte records, one block or a
+// chain of blocks) are consecutive and so are its output rows, so no search is needed:
+// consecutive lanes copy consecutive rows, four rows per lane in flight.  gridDim.y CTAs
+// share a block of units, each takes a slice of the units.
+__global__ void __launch_bounds__(SCAN_THREADS)
+strip_copy_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
+                  const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
+                  const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
+                  const unsigned long long* __restrict__ block_base,
+                  const long long* __restrict__ seg_tile_start, int n_seg,
+                  const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
+                  uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
+                  long long scr_cap, int64_t* __restrict__ seg_out_end) {
+    __shared__ uint32_t excl[SCAN_BLOCK];
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
+    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
+    const unsigned long long base = block_base[blockIdx.x];
+    const uint32_t block_total = gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start,
+                                                   n_seg, seg_out_end, blockIdx.y == 0, excl, wsum);
+    if (out_cap == 0 || block_total == 0) return;
+    const int n_units = (int)(blk_hi - blk_lo);
+    const int upc = (n_units + (int)gridDim.y - 1) / (int)gridDim.y;       // this CTA's units
+    const int u_lo = (int)blockIdx.y * upc;
+    const int u_hi = min(u_lo + upc, n_units);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int U = 4;                            // rows per lane in flight
+    for (int u = u_lo + warp; u < u_hi; u += SCAN_THREADS / 32) {
+        uint32_t left = u + 1 < n_units ? excl[u + 1] - excl[u] : block_total - excl[u];
+        if (left == 0) continue;
+        unsigned long long d = base + excl[u];
+        unsigned long long off = tile_off[blk_lo + u];
+        uint32_t cnt = first_cnt[blk_lo + u];
+        int32_t nx = unit_next[blk_lo + u];
+        for (;;) {
+            if (cnt > left) cnt = left;
+            for (uint32_t r0 = 0; r0 < cnt; r0 += U * 32) {
+                uint32_t v[U][3];
+                bool ok[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const uint32_t r = r0 + j * 32 + lane;
+                    ok[j] = r < cnt && off + r < (unsigned long long)scr_cap && d + r < (unsigned long long)out_cap;
+                    if (ok[j]) {
+                        const uint32_t* row = scr + (off + r) * 3;
+                        v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    if (ok[j]) {
+                        const unsigned long long o = d + r0 + j * 32 + lane;
+                        out_start[o] = (int32_t)v[j][0];
+                        out_end[o] = v[j][1];
+                        out_order[o] = (int32_t)v[j][2];
+                    }
+                }
+            }
+            left -= cnt;
+            d += cnt;
+            if (left == 0 || nx < 0 || (uint32_t)nx >= pool_cap) break;    // (a full pool loses rows: counted, not stored)
+            const BlockRec rec = pool[nx];
+            off = rec.off;
+            cnt = rec.cnt;
+            nx = rec.next;
         }
     }
 }
@@ -525,11 +596,13 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
                                                                           done, result);
     MEMO_CUDA_TRY(cudaGetLastError());
     {
-        // ~8 CTAs per SM in total: every block of units is copied by `split` CTAs
-        long long split = (8ll * device_sm_count() + plan.n_blocks - 1) / plan.n_blocks;
+        // every block of units is copied by `split` CTAs; all CTAs resident at once (8 x 256
+        // threads per SM): a few CTAs left over for a second wave would double the kernel's time
+        long long split = 8ll * device_sm_count() / plan.n_blocks;
         if (split < 1) split = 1;
         if (split > 32) split = 32;
-        strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
+        static const int variant = getenv("MEMO_GATHER") ? atoi(getenv("MEMO_GATHER")) : 0;     // tuning
+        (variant == 1 ? strip_copy_kernel : strip_gather_kernel)<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
             P.tile_cnt, P.tile_off, P.first_cnt, P.unit_next, P.pool, P.pool_cap, plan.n_units, partial,
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
             seg_out_end);
