@@ -214,3 +214,22 @@ def test_sharded_build_equals_whole_on_oracle():
             parts.append(co.index_build(vals[p.buf_lo:p.buf_hi], recs, True, segs=segs))
         for j in range(4):
             assert np.array_equal(np.concatenate([q[j] for q in parts]), whole[j]), world
+
+
+def test_query_rows_for_range_on_oracle():
+    """a position range answered from its own rows plus a right halo of
+    k_max - 1 positions equals the slice of the whole-window answer (oracle only)."""
+    from memo_b200 import shard
+    L, C = 3000, 7
+    vals = mo.synth_dap(L, C, seed=5, dense=True)
+    _, s, e, c = mo.index_build(vals, [("chrH", L)], True)
+    ks = (3, 31, 64)
+    for world in (2, 3, 5):
+        for k in ks:
+            whole = mo.query(s, e, c, 0, L, k, C + 1, False)
+            parts = []
+            for rank in range(world):
+                lo, hi = shard.shard_range(L, world, rank)
+                a, b = shard.query_rows_for_range(s, lo, hi, max(ks))
+                parts.append(mo.query(s[a:b], e[a:b], c[a:b], lo, hi, k, C + 1, False))
+            assert np.array_equal(np.concatenate(parts), whole), (world, k)
