@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.002)
 
     def stop(self):
         self._stop_evt.set()
