@@ -223,6 +223,36 @@ def test_index_large_values_uint32_end():
     assert_index_equal(got, want, "u32")
 
 
+GRCH38 = (248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+          138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+          83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415)
+
+
+@pytest.mark.parametrize("C,order", [(9, True), (9, False), (93, True)])
+def test_index_whole_genome_layout_scaled(C, order):
+    """BASELINE configs[4]'s layout at 1/2000 scale (C = 9) / 1/20000 (C = 93): the 24 GRCh38
+    primary records in one DAP, every record with its own synthetic matching statistics;
+    index rows (incl. the chr-end rows of all 24 records) bit-exact against the C port of the
+    reference algorithm, and one k-mer query per record against the oracle."""
+    from oracle import c_oracle as co
+    api = _api()
+    scale = 2000 if C == 9 else 20000
+    records = [(f"chr{i + 1}", n // scale) for i, n in enumerate(GRCH38)]
+    parts = [mo.synth_dap(n, C, seed=100 + i) for i, (_, n) in enumerate(records)]
+    vals = np.concatenate(parts)
+    want = co.index_build(vals, records, order)
+    res, got = gpu_index(vals, records, order)
+    assert_index_equal(got, want, "whole genome layout")
+    # queries: rows of one record, whole record window (past its end as well)
+    for rid in (0, 7, 23):
+        m = want[0] == rid
+        n_rec = records[rid][1]
+        for membership in ((False,) if order else (True,)):
+            w = mo.query(want[1][m], want[2][m], want[3][m], 0, n_rec + 50, 31, C + 1, membership)
+            g, _ = gpu_query(want[1][m], want[2][m], want[3][m], 0, n_rec + 50, 31, C + 1, membership)
+            assert np.array_equal(g, w), (rid, membership)
+
+
 # ------------------------------------------------------------------ queries
 @pytest.mark.parametrize("C,membership", [(9, False), (9, True), (93, False), (93, True), (40, True)])
 def test_query_vs_oracle(C, membership):
