@@ -1,4 +1,4 @@
-// k-mer conservation query for n_docs <= 255 on sm_100a: bit-plane tiles.
+// k-mer conservation (n_docs <= 255) and membership queries on sm_100a: bit-plane tiles.
 //
 // Replaces the reference's src/memo_query.py memo_init :42-55, memo_query :57-63
 // and the argmax of print_res :70 (see query.cu for the definition):
@@ -13,8 +13,8 @@
 // positions, i.e. it ORs one or two 32-bit words (k <= 33) instead of painting
 // 30 cells.  When the tile's rows are in, one lane per 32-position word column
 // walks the planes in ascending order (first plane with the bit set = the
-// minimum), keeps the result as 8 binary digit planes and expands those into the
-// 32 output bytes of its positions: two 128-bit coalesced stores per lane.
+// minimum), keeps the result as B binary digit planes (n_docs < 2^B) and expands those
+// into the 32 output bytes of its positions: two 128-bit coalesced stores per lane.
 //
 // Membership (-m) uses the same planes (one per genome) and row walk; its result IS a
 // bitmap, transposed: one lane per word column transposes 32 planes x 32 positions in
@@ -24,8 +24,11 @@
 // Every WARP is an independent stream (no __syncthreads, no bounds pass): it
 // takes runs of consecutive tiles from an atomic counter, finds the first row of
 // the run with one cooperative 32-ary search and from then on walks the rows
-// forward 64 at a time (coalesced, next batch in flight) -- the first row of the
-// next tile is seen while the current tile's halo rows go by.
+// forward 128 at a time (one 128-bit load per array and lane, next batch in
+// flight) -- the first row of the next tile is seen while the current tile's halo
+// rows go by.  A tile that turns out heavy (a dense stretch of the index, e.g. the
+// start of a record) is handed on in pieces through a small record table in the
+// workspace, so that no single warp decides the kernel's time.
 #include <stdlib.h>
 
 #include "common.cuh"
