@@ -152,22 +152,24 @@ __device__ __forceinline__ uint32_t gather_block_scan(
     return block_total;
 }
 
-// A unit (strip) wrote one block of scratch rows, or a chain of them.  A CTA
-// stages the metadata of its block of 1024 units in shared memory, and its
-// threads then copy output rows independently (consecutive threads, consecutive
-// output rows): owner unit by binary search in the block's exclusive scan,
-// source row from the unit's block chain.  gridDim.y CTAs share a block of units,
-// each copying a contiguous slice of the block's rows.
+// A unit (strip) wrote one block of scratch rows, or a chain of them.  A CTA stages the
+// metadata of its block of 1024 units in shared memory; gridDim.y CTAs share a block, each
+// copying a contiguous slice of the block's output rows in chunks of consecutive rows per
+// warp (consecutive lanes, consecutive output rows).  One search for the unit of a chunk's
+// first row (warp uniform), after that every lane walks the units forward as its rows
+// advance: a few instructions per row (a binary search per row made this kernel
+// instruction bound: 5 warp instructions per row).  The source row comes from the unit's
+// block chain.
 __global__ void __launch_bounds__(SCAN_THREADS)
 strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
-                    const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
-                    const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
-                    const unsigned long long* __restrict__ block_base,
-                    const long long* __restrict__ seg_tile_start, int n_seg,
-                    const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
-                    uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                    long long scr_cap, int64_t* __restrict__ seg_out_end) {
-    __shared__ uint32_t excl[SCAN_BLOCK];
+                  const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
+                  const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
+                  const unsigned long long* __restrict__ block_base,
+                  const long long* __restrict__ seg_tile_start, int n_seg,
+                  const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
+                  uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
+                  long long scr_cap, int64_t* __restrict__ seg_out_end) {
+    __shared__ uint32_t excl[SCAN_BLOCK + 1];
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     __shared__ uint32_t s_fcnt[SCAN_BLOCK];
     __shared__ int32_t s_next[SCAN_BLOCK];
@@ -184,127 +186,66 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
         s_fcnt[u] = first_cnt[blk_lo + u];
         s_next[u] = unit_next[blk_lo + u];
     }
+    if (threadIdx.x == 0) excl[n_units] = block_total;          // upper end of the last unit
     __syncthreads();
-    // this CTA's slice of the block's rows
+    // this CTA's slice of the block's rows, in chunks of CH consecutive rows per warp
     const uint32_t lo = (uint32_t)((unsigned long long)block_total * blockIdx.y / gridDim.y);
     const uint32_t hi = (uint32_t)((unsigned long long)block_total * (blockIdx.y + 1) / gridDim.y);
-
-    // scratch row of the block's output row d (0xFF..F = not stored)
-    auto source = [&](uint32_t d) -> unsigned long long {
-        int a = 0, b = n_units - 1;                 // last unit with excl[u] <= d
-        while (a < b) {
-            const int m = (a + b + 1) >> 1;
-            if (excl[m] <= d) a = m; else b = m - 1;
-        }
-        uint32_t r = d - excl[a];
-        unsigned long long off = s_off[a];
-        uint32_t cnt = s_fcnt[a];
-        int32_t nx = s_next[a];
-        while (r >= cnt) {                          // continue in the unit's next block
-            if (nx < 0 || (uint32_t)nx >= pool_cap) return ~0ull;
-            r -= cnt;
-            const BlockRec rec = pool[nx];
-            off = rec.off;
-            cnt = rec.cnt;
-            nx = rec.next;
-        }
-        const unsigned long long src = off + r;
-        return src < (unsigned long long)scr_cap ? src : ~0ull;
-    };
-
-    constexpr int U = 4;                            // rows per thread in flight
-    for (uint32_t d0 = lo + threadIdx.x; d0 < hi; d0 += U * SCAN_THREADS) {
-        unsigned long long src[U];
-        uint32_t v[U][3];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const uint32_t d = d0 + j * SCAN_THREADS;
-            src[j] = d < hi ? source(d) : ~0ull;
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (src[j] != ~0ull) {
-                const uint32_t* row = scr + src[j] * 3;
-                v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const unsigned long long d = base + d0 + j * SCAN_THREADS;
-            if (src[j] != ~0ull && d < (unsigned long long)out_cap) {
-                out_start[d] = (int32_t)v[j][0];
-                out_end[d] = v[j][1];
-                out_order[d] = (int32_t)v[j][2];
-            }
-        }
-    }
-}
-
-// Variant: one warp per unit.  A unit's scratch rows (12-byte records, one block or a
-// chain of blocks) are consecutive and so are its output rows, so no search is needed:
-// consecutive lanes copy consecutive rows, four rows per lane in flight.  gridDim.y CTAs
-// share a block of units, each takes a slice of the units.
-__global__ void __launch_bounds__(SCAN_THREADS)
-strip_copy_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
-                  const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
-                  const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
-                  const unsigned long long* __restrict__ block_base,
-                  const long long* __restrict__ seg_tile_start, int n_seg,
-                  const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
-                  uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                  long long scr_cap, int64_t* __restrict__ seg_out_end) {
-    __shared__ uint32_t excl[SCAN_BLOCK];
-    __shared__ uint32_t wsum[SCAN_THREADS / 32];
-    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
-    const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
-    const unsigned long long base = block_base[blockIdx.x];
-    const uint32_t block_total = gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start,
-                                                   n_seg, seg_out_end, blockIdx.y == 0, excl, wsum);
-    if (out_cap == 0 || block_total == 0) return;
-    const int n_units = (int)(blk_hi - blk_lo);
-    const int upc = (n_units + (int)gridDim.y - 1) / (int)gridDim.y;       // this CTA's units
-    const int u_lo = (int)blockIdx.y * upc;
-    const int u_hi = min(u_lo + upc, n_units);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int U = 4;                            // rows per lane in flight
-    for (int u = u_lo + warp; u < u_hi; u += SCAN_THREADS / 32) {
-        uint32_t left = u + 1 < n_units ? excl[u + 1] - excl[u] : block_total - excl[u];
-        if (left == 0) continue;
-        unsigned long long d = base + excl[u];
-        unsigned long long off = tile_off[blk_lo + u];
-        uint32_t cnt = first_cnt[blk_lo + u];
-        int32_t nx = unit_next[blk_lo + u];
-        for (;;) {
-            if (cnt > left) cnt = left;
-            for (uint32_t r0 = 0; r0 < cnt; r0 += U * 32) {
-                uint32_t v[U][3];
-                bool ok[U];
+    constexpr uint32_t CH = 32 * U * 4;
+    for (uint32_t c0 = lo + warp * CH; c0 < hi; c0 += (SCAN_THREADS / 32) * CH) {
+        const uint32_t c1 = min(c0 + CH, hi);
+        int u = 0;
+        {
+            int a = 0, b = n_units - 1;             // last unit with excl[u] <= c0 (skips empty ones)
+            while (a < b) {
+                const int m = (a + b + 1) >> 1;
+                if (excl[m] <= c0) a = m; else b = m - 1;
+            }
+            u = a;
+        }
+        for (uint32_t b0 = c0; b0 < c1; b0 += 32 * U) {
+            unsigned long long src[U];
+            uint32_t v[U][3];
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    const uint32_t r = r0 + j * 32 + lane;
-                    ok[j] = r < cnt && off + r < (unsigned long long)scr_cap && d + r < (unsigned long long)out_cap;
-                    if (ok[j]) {
-                        const uint32_t* row = scr + (off + r) * 3;
-                        v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
+            for (int j = 0; j < U; ++j) {
+                const uint32_t d = b0 + j * 32 + lane;
+                src[j] = ~0ull;
+                if (d < c1) {
+                    while (excl[u + 1] <= d) ++u;   // d < block_total = excl[n_units]: stops in range
+                    uint32_t r = d - excl[u];
+                    unsigned long long off = s_off[u];
+                    uint32_t cnt = s_fcnt[u];
+                    int32_t nx = s_next[u];
+                    bool ok = true;
+                    while (r >= cnt) {              // continue in the unit's next block
+                        if (nx < 0 || (uint32_t)nx >= pool_cap) { ok = false; break; }
+                        r -= cnt;
+                        const BlockRec rec = pool[nx];
+                        off = rec.off;
+                        cnt = rec.cnt;
+                        nx = rec.next;
                     }
-                }
-#pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    if (ok[j]) {
-                        const unsigned long long o = d + r0 + j * 32 + lane;
-                        out_start[o] = (int32_t)v[j][0];
-                        out_end[o] = v[j][1];
-                        out_order[o] = (int32_t)v[j][2];
-                    }
+                    if (ok && off + r < (unsigned long long)scr_cap) src[j] = off + r;
                 }
             }
-            left -= cnt;
-            d += cnt;
-            if (left == 0 || nx < 0 || (uint32_t)nx >= pool_cap) break;    // (a full pool loses rows: counted, not stored)
-            const BlockRec rec = pool[nx];
-            off = rec.off;
-            cnt = rec.cnt;
-            nx = rec.next;
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                if (src[j] != ~0ull) {
+                    const uint32_t* row = scr + src[j] * 3;
+                    v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const unsigned long long d = base + b0 + j * 32 + lane;
+                if (src[j] != ~0ull && d < (unsigned long long)out_cap) {
+                    out_start[d] = (int32_t)v[j][0];
+                    out_end[d] = v[j][1];
+                    out_order[d] = (int32_t)v[j][2];
+                }
+            }
         }
     }
 }
@@ -601,8 +542,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         long long split = 8ll * device_sm_count() / plan.n_blocks;
         if (split < 1) split = 1;
         if (split > 32) split = 32;
-        static const int variant = getenv("MEMO_GATHER") ? atoi(getenv("MEMO_GATHER")) : 0;     // tuning
-        (variant == 1 ? strip_copy_kernel : strip_gather_kernel)<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
+        strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
             P.tile_cnt, P.tile_off, P.first_cnt, P.unit_next, P.pool, P.pool_cap, plan.n_units, partial,
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
             seg_out_end);
