@@ -333,7 +333,9 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
         if (T * row_bytes + 160 + 128 * plan->kpl > budget) T = (budget - 160 - 128 * plan->kpl) / row_bytes;
         if (T < 1) T = 1;
-        long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : 128;
+        // about 128 compare rows per strip, a whole number of chunks (predecessor row included)
+        long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records
+                                                           : (128 / T > 1 ? 128 / T : 1) * T - 1;
         if (R < 1) R = 1;
         plan->R = (int)R;
         // (slots of lanes past the last column read up to 128 * kpl bytes beyond a row)
