@@ -1,0 +1,79 @@
+"""Live differential: the oracle against the UNMODIFIED reference scripts, run as child
+processes where the reference tree exists (the build container: /root/reference, or
+$MEMO_REFERENCE).  Skipped elsewhere -- the committed goldens (tests/golden/) carry the
+same comparison to the GPU box.  Fresh seeds every time the file changes, so this is a
+second, independent pin of the oracle next to the goldens."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import memo_oracle as mo
+
+REF = os.environ.get("MEMO_REFERENCE", "/root/reference")
+SRC = os.path.join(REF, "src")
+pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(SRC, "dap_to_bed.py")),
+                                reason="reference tree not present")
+
+
+def _random_case(rng, valid):
+    n_rec = int(rng.integers(1, 4))
+    lens = [int(rng.integers(2, 40)) for _ in range(n_rec)]
+    C = int(rng.integers(1, 7))
+    L = sum(lens)
+    if valid:
+        parts = [mo.synth_dap(n, C, seed=int(rng.integers(1, 1 << 30)), dense=True) for n in lens]
+        vals = np.concatenate(parts)
+    else:
+        vals = rng.integers(0, 12, size=(L, C))
+    return [(f"rec{i}", n) for i, n in enumerate(lens)], vals.astype(np.int64)
+
+
+def _run_reference_index(tmp_path, records, vals, order):
+    fai = tmp_path / "pivot.fa.fai"
+    fai.write_text("".join(f"{h}\t{n}\t7\t{n}\t{n + 1}\n" for h, n in records))
+    dap = tmp_path / "dap.txt"
+    dap.write_text("".join(f"{p} " + " ".join(str(v) for v in row) + "\n" for p, row in enumerate(vals)))
+    argv = [sys.executable, os.path.join(SRC, "dap_to_bed.py"), "--mem", "--overlap", "--fai", str(fai),
+            "--dap", str(dap)] + (["--order"] if order else [])
+    return subprocess.run(argv, check=True, capture_output=True, text=True).stdout
+
+
+def _bed_text(records, rows):
+    rec, s, e, c = rows
+    return "".join(f"{records[r][0]}\t{a}\t{b}\t{o}\n" for r, a, b, o in zip(rec, s, e, c))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_index_against_live_reference(seed, tmp_path):
+    rng = np.random.default_rng(7000 + seed)
+    records, vals = _random_case(rng, valid=seed % 2 == 0)
+    for order in (True, False):
+        want = _run_reference_index(tmp_path, records, vals, order)
+        assert _bed_text(records, mo.index_build(vals, records, order)) == want, (seed, order)
+
+
+def test_query_against_live_reference(tmp_path):
+    pytest.importorskip("numba")
+    pa = pytest.importorskip("pyarrow")
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(99)
+    L, C = 400, 5
+    records = [("chrQ", L)]
+    vals = mo.synth_dap(L, C, seed=4242, dense=True).astype(np.int64)
+    for membership in (False, True):
+        rec, s, e, c = mo.index_build(vals, records, not membership)
+        table = pa.table({"f0": pa.array(["chrQ"] * len(s), pa.utf8()), "f1": pa.array(s, pa.int64()),
+                          "f2": pa.array(e, pa.int64()), "f3": pa.array(c, pa.int64())})
+        pq_path = tmp_path / ("m.parquet" if membership else "c.parquet")
+        pq.write_table(table, pq_path, compression="ZSTD")
+        for (qs, qe, k) in ((0, L, 31), (37, 311, 5), (L - 9, L + 20, 12)):
+            out = tmp_path / "q.txt"
+            argv = [sys.executable, os.path.join(SRC, "memo_query.py"), "-b", str(pq_path), "-r", f"chrQ:{qs}-{qe}",
+                    "-k", str(k), "-n", str(C + 1), "-o", str(out)] + (["-m"] if membership else [])
+            subprocess.run(argv, check=True, capture_output=True, text=True)
+            got = mo.query(s, e, c, qs, qe, k, C + 1, membership)
+            text = mo.format_membership(got) if membership else mo.format_conservation(got)
+            assert out.read_text() == text, (membership, qs, qe, k)
