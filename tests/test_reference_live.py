@@ -77,3 +77,26 @@ def test_query_against_live_reference(tmp_path):
             got = mo.query(s, e, c, qs, qe, k, C + 1, membership)
             text = mo.format_membership(got) if membership else mo.format_conservation(got)
             assert out.read_text() == text, (membership, qs, qe, k)
+
+
+def test_parquet_stage_against_live_reference(tmp_path):
+    """parquet_compress_bed.py of the reference and of memo_b200 on the same BED: equal
+    tables, equal schema (names, types, no schema metadata), ZSTD (table
+    equality is the contract, the file embeds a writer version string)."""
+    pytest.importorskip("pandas")
+    pq = pytest.importorskip("pyarrow.parquet")
+    rng = np.random.default_rng(5)
+    records, vals = _random_case(rng, valid=True)
+    bed = tmp_path / "idx.bed"
+    bed.write_text(_bed_text(records, mo.index_build(vals, records, True)))
+    ref_out, our_out = tmp_path / "ref.parquet", tmp_path / "our.parquet"
+    subprocess.run([sys.executable, os.path.join(SRC, "parquet_compress_bed.py"), "-f", str(bed), "-o", str(ref_out)],
+                   check=True, capture_output=True, text=True)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-m", "memo_b200.parquet_compress_bed", "-f", str(bed), "-o", str(our_out)],
+                   check=True, capture_output=True, text=True, cwd=root)
+    a, b = pq.read_table(str(ref_out)), pq.read_table(str(our_out))
+    assert a.schema.equals(b.schema, check_metadata=True), (a.schema, b.schema)
+    assert a.equals(b)
+    ma, mb = pq.ParquetFile(str(ref_out)).metadata, pq.ParquetFile(str(our_out)).metadata
+    assert ma.row_group(0).column(1).compression == mb.row_group(0).column(1).compression == "ZSTD"
