@@ -100,3 +100,15 @@ def test_parquet_stage_against_live_reference(tmp_path):
     assert a.equals(b)
     ma, mb = pq.ParquetFile(str(ref_out)).metadata, pq.ParquetFile(str(our_out)).metadata
     assert ma.row_group(0).column(1).compression == mb.row_group(0).column(1).compression == "ZSTD"
+
+
+@pytest.mark.parametrize("C,order", [(9, True), (9, False), (40, True)])
+def test_c_port_against_live_reference_at_scale(C, order, tmp_path):
+    """The C port (bench.py's cpu_baseline / --impl reference arm) on a synthetic
+    HPRC-shaped DAP of 40 k rows in two records, against the reference script itself."""
+    from oracle import c_oracle as co
+    lens = [25000, 15000]
+    records = [(f"chr{i + 1}", n) for i, n in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=31 + i) for i, n in enumerate(lens)]).astype(np.int64)
+    want = _run_reference_index(tmp_path, records, vals, order)
+    assert _bed_text(records, co.index_build(vals, records, order)) == want
