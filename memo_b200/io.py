@@ -2,7 +2,9 @@
 writers and readers.  Format conversion only -- no index arithmetic here."""
 from __future__ import annotations
 
+import re
 import sys
+import warnings
 from typing import Sequence, Tuple
 
 import numpy as np
@@ -13,6 +15,8 @@ import pyarrow.dataset as pads
 import pyarrow.parquet as pq
 
 from ._lib import MemoError
+
+_NOT_LENGTHS = re.compile(rb"[^0-9\s]")
 
 INDEX_SCHEMA = pa.schema([("f0", pa.utf8()), ("f1", pa.int64()), ("f2", pa.int64()), ("f3", pa.int64())])
 
@@ -62,10 +66,11 @@ def read_lengths_columns(paths: Sequence[str], threads: int = 8) -> np.ndarray:
             data = fh.read()
         if b">" in data:
             data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b">"))
-        try:
-            col = np.array(data.split(), dtype=np.int64)
-        except ValueError as exc:                                # int() in the reference
-            raise ValueError(f"invalid literal for int() in {path}") from exc
+        if _NOT_LENGTHS.search(data):                            # int() in the reference
+            raise ValueError(f"invalid literal for int() in {path}")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            col = np.fromstring(data.decode("ascii"), dtype=np.int64, sep=" ")     # any whitespace separates
         if col.size and (col.min() < 0 or col.max() > 2**31 - 1):
             raise MemoError("DAP lengths must be in [0, 2^31)")
         return col.astype(np.int32)
