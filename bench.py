@@ -1,8 +1,10 @@
 #!/usr/bin/env python3
 """bench.py -- MEMO hot path on B200: pivot bp/s for conservation index build +
-k=31 window query (BASELINE.json configs[1]: 10 genomes x 100 Mbp, synthetic
-HPRC-shaped DAP), with the HBM roofline of the dominant kernel, an end-to-end
-leg through the host-buffer API, and the CPU port timed on the same box.
+k=31 window query on BASELINE.json configs[3] -- a chr1-sized pivot record
+(248 956 422 bp) x 94 genomes, synthetic HPRC-shaped DAP -- on 1 GPU, or cut into
+N position shards on N GPUs (strong scaling), with the HBM roofline of the
+dominant kernel, an end-to-end leg through the host-buffer API, parity against
+the C port of the reference algorithm, and that port timed on the same box.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -14,6 +16,7 @@ the shard's window on the freshly built index rows.  value = total pivot bp over
 all ranks / max-over-ranks device time.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -23,8 +26,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEED = 20240611 + 1            # seed = 20240611 + config index
+SEED0 = 20240611               # seed = 20240611 + config index
 KH = 128                       # right halo rows kept for queries (k <= 129)
+CHR1 = 248_956_422
 
 
 def load_peaks():
@@ -37,26 +41,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-CAPTURED = {9: 100_000_000, 93: 10_000_000}     # pivot bp of the workloads profiles/traffic.json was captured on
-
-
-def ncu_traffic(cols, whole=False, rows=None):
-    """dram bytes (read + write) per launch of the streaming kernel (or of the whole
-    index build) of the default workload, from the committed `ncu --set full` capture
-    (profiles/traffic.json, scripts/ncu_traffic.py), or None."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
-    if rows is not None and CAPTURED.get(cols) != rows:
-        return None                                  # per launch of a different workload
+def profiled_traffic(key):
+    """DRAM bytes (read + write) per launch from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json, scripts/ncu_traffic.py), or
+    None.  A profile lookup, not a measurement of this run: the source is named
+    in the line."""
     try:
-        data = json.load(open(path))
-        if whole:
-            return data.get(f"index_build_c{cols}")
-        for k in data.get(f"index_build_c{cols}_kernels", []):
-            if "narrow_kernel" in k["kernel"] or "wide_kernel" in k["kernel"]:
-                return k["dram_bytes"]
+        data = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return data.get(key), data.get("_source")
     except Exception:
-        pass
-    return None
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -108,26 +102,33 @@ class ClockSampler(threading.Thread):
 # CPU arm: the oracle's C port on host cores (the reference itself is Python and
 # does not exist on the GPU box; see DESIGN.md "measurement")
 # ---------------------------------------------------------------------------
-def cpu_port_run(dap_np, rec_len, row0, k, n_docs, threads):
-    """Index build (conservation) + k-mer query over the rows of `dap_np` (a
-    slice [row0, row0+n) of one record), cut into `threads` slices with a
-    one-row halo (exact for matching statistics).  Returns (seconds, n_out)."""
+def cpu_port_run(dap_np, rec_len, row0, k, n_docs, threads, order=True, halo_first=False, do_query=True):
+    """Index build + k-mer query over rows [row0, row0 + n) of one record held in
+    `dap_np` (with halo_first, dap_np[0] is row row0 - 1, the halo of a slice that
+    starts inside the record), cut into `threads` slices with a one-row halo
+    (exact for matching statistics).  Returns (seconds, n_out, query, rows)."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     from oracle import c_oracle as co
 
-    n, C = dap_np.shape
+    off = 1 if halo_first else 0
+    n, C = dap_np.shape[0] - off, dap_np.shape[1]
     recs = [("chrS", rec_len)]
     cuts = [row0 + (n * i) // threads for i in range(threads + 1)]
 
     def work(i):
         a, b = cuts[i], cuts[i + 1]
-        lo = a - 1 if a > row0 else a
+        if b <= a:
+            return tuple(np.zeros(0, dtype=np.int64) for _ in range(4))
+        lo = a - 1 if a > 0 else a          # halo row (the record's previous row)
         segs = co.make_segs(recs, b - a, pos_first=a, row0=a - lo, primed_first=(a == 0),
                             chr_end_last=(b == rec_len))
-        cap = int((b - a) * C * 0.05) + 4 * C
-        r = co.index_build(dap_np[lo - row0:b - row0], recs, True, segs=segs, cap=cap)
-        return r
+        cap = int((b - a) * C * 0.06) + 4 * C
+        while True:
+            r = co.index_build(dap_np[lo - row0 + off:b - row0 + off], recs, order, segs=segs, cap=cap)
+            if r[1].size < cap:
+                return r
+            cap *= 2
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
@@ -135,66 +136,402 @@ def cpu_port_run(dap_np, rec_len, row0, k, n_docs, threads):
     f1 = np.concatenate([p[1] for p in parts])
     f2 = np.concatenate([p[2] for p in parts])
     f3 = np.concatenate([p[3] for p in parts])
-    qcuts = cuts
 
     def qwork(i):
-        return co.query(f1, f2, f3, qcuts[i], qcuts[i + 1], k, n_docs, False)
+        return co.query(f1, f2, f3, cuts[i], cuts[i + 1], k, n_docs, not order)
 
-    with ThreadPoolExecutor(threads) as ex:
-        outs = list(ex.map(qwork, range(threads)))
+    outs = None
+    if do_query:
+        with ThreadPoolExecutor(threads) as ex:
+            outs = np.concatenate(list(ex.map(qwork, range(threads))))
     dt = time.perf_counter() - t0
-    return dt, int(f1.size), np.concatenate(outs), (f1, f2, f3)
+    return dt, int(f1.size), outs, (f1, f2, f3)
+
+
+def workload_config(args, n_gpus):
+    memb = args.membership
+    rows, genomes = args.rows, args.cols + 1
+    if args.cols == 93 and rows == CHR1 and not memb:
+        tag = "BASELINE configs[3]: HPRC-shaped chr1 (248 956 422 bp pivot) x 94 genomes"
+    elif args.cols == 9 and rows == 100_000_000 and not memb:
+        tag = "BASELINE configs[1]: 10 genomes x 100 Mbp pivot"
+    elif memb:
+        tag = "BASELINE configs[2]-shaped: membership index (-m) and per-genome presence bitmaps"
+    else:
+        tag = "non-default shape"
+    what = "membership index build + membership" if memb else "conservation index build +"
+    return {"workload": f"{tag}; synthetic HPRC-shaped DAP, {genomes} genomes x {rows} bp pivot record "
+                        f"cut into {n_gpus} position shard(s), {what} k={args.k} window query over "
+                        "every shard",
+            "genomes": genomes, "pivot_bp": rows, "pivot_bp_per_gpu": rows // n_gpus, "k": args.k,
+            "partition": f"position ranges x{n_gpus} of one record, 1-row left halo, {KH}-row right halo",
+            "l2": f"inputs ({rows // n_gpus * args.cols * 4 / 1e9:.2f} GB DAP per GPU) are larger than L2; "
+                  "no flush needed",
+            "seed": seed_of(args)}
+
+
+def seed_of(args):
+    if args.cols == 9 and not args.membership:
+        return SEED0 + 1
+    if args.membership:
+        return SEED0 + 2
+    return SEED0 + 3
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle import memo_oracle as mo
+    from oracle import c_oracle as co
     C, k = args.cols, args.k
     cores = os.cpu_count() or 1
     sample = min(args.rows, args.ref_sample_rows)
-    dap = mo.synth_dap(args.rows, C, SEED, row0=0, rows=sample)
+    dap = co.synth_dap(args.rows, C, seed_of(args), row0=0, rows=sample, threads=cores)
     times = []
     for i in range(args.warmup + args.steps):
-        dt, n_out, _, _ = cpu_port_run(dap, args.rows, 0, k, C + 1, cores)
+        dt, n_out, _, _ = cpu_port_run(dap, args.rows, 0, k, C + 1, cores, order=not args.membership)
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = sample * len(times) / total
     line = {
-        "impl": "reference", "metric": "pivot bp/s (conservation index build + k-mer query)",
+        "impl": "reference", "metric": "pivot bp/s (%s index build + k-mer query)" %
+                                       ("membership" if args.membership else "conservation"),
         "value": value, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample} rows of the workload per step; C port of the "
-                                   "reference algorithm (oracle/memo_oracle.c), one slice per core"},
+                                   "reference algorithm (oracle/memo_oracle.c), one slice per core; the "
+                                   "reference itself is Python (no compiled source to build) and is "
+                                   "absent on this box: BASELINE.md records its rate"},
         "e2e": {"value": value, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, n_gpus):
-    memb = getattr(args, "membership", False)
-    if args.cols == 9 and args.rows == 100_000_000 and not memb:
-        tag = "BASELINE configs[1]"
-    elif memb:
-        tag = "BASELINE configs[2]-shaped: membership index (-m) and per-genome presence bitmaps"
-    elif args.cols == 93:
-        tag = "BASELINE configs[3]-shaped shard: 94 genomes"
+# ---------------------------------------------------------------------------
+class Workload:
+    """One record of `rec_len` rows x C columns, position-sharded over the ranks;
+    this rank's shard resident on its device, outputs sized by a counting run."""
+
+    def __init__(self, rec_len, C, k, membership, seed, rank, world, dev, tuning):
+        import torch
+        from memo_b200 import api, shard, _lib
+        self.torch, self.api = torch, api
+        self.rec_len, self.C, self.k, self.membership = rec_len, C, k, membership
+        self.n_docs = C + 1
+        self.rank, self.world, self.dev, self.tuning, self.seed = rank, world, dev, tuning, seed
+        self.lo, self.hi = shard.shard_range(rec_len, world, rank)
+        self.Lr = self.hi - self.lo
+        self.buf_lo = self.lo - 1 if self.lo > 0 else self.lo      # 1-row left halo
+        self.buf_hi = min(self.hi + KH, rec_len)                   # right halo for the query
+        self.dap = api.synth_dap(rec_len, C, seed, row0=self.buf_lo, rows=self.buf_hi - self.buf_lo, device=dev)
+        segs = [api.Segment(row_begin=self.lo - self.buf_lo, n_rows=self.Lr, pos0=self.lo, rec_len=rec_len,
+                            rec_id=0, flags=(api.MEMO_SEG_PRIMED if self.lo == 0 else 0) |
+                                            (api.MEMO_SEG_CHR_END if self.hi == rec_len else 0))]
+        if self.buf_hi > self.hi:
+            segs.append(api.Segment(row_begin=self.hi - self.buf_lo, n_rows=self.buf_hi - self.hi,
+                                    pos0=self.hi, rec_len=rec_len, rec_id=0, flags=0))
+        self.segs = segs
+        self.order = not membership
+        self.builder = api.IndexBuilder(dev)
+        self.seg_out_end = torch.zeros(len(segs), dtype=torch.int64, device=dev)
+        self.builder.launch(self.dap, C, segs, self.order, None, self.seg_out_end, **tuning)   # counting run
+        self.n_all, irregular, _ = self.builder.result()
+        assert not irregular, "synthetic DAP must be valid matching statistics"
+        self.out = tuple(torch.empty(self.n_all + 16, dtype=torch.int32, device=dev) for _ in range(3))
+        self.q_out = torch.empty((self.Lr, (self.n_docs + 31) // 32), dtype=torch.int32, device=dev) \
+            if membership else torch.empty(self.Lr, dtype=torch.uint8, device=dev)
+        self.counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        self.q_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.q_ws = torch.empty(max(_lib.load().memo_query_workspace_bytes(self.Lr), 1), dtype=torch.uint8,
+                                device=dev)
+
+    def build(self):
+        self.builder.launch(self.dap, self.C, self.segs, self.order, self.out, self.seg_out_end, **self.tuning)
+
+    def query(self):
+        n, o, api = self.n_all, self.out, self.api
+        fn = api.query_membership if self.membership else api.query_conservation
+        fn(o[0][:n], o[1][:n], o[2][:n], self.lo, self.hi, self.k, self.n_docs, out=self.q_out,
+           check=False, status=self.q_status, workspace=self.q_ws)
+
+    def step(self, ev=None):
+        # nothing in here waits for the device: the row count is known from the sizing
+        # run (and re-checked after the timed region), the query reads the fresh rows
+        import torch.distributed as dist
+        if ev:
+            ev[0].record()
+        self.build()
+        if ev:
+            ev[1].record()
+        if self.world > 1:                               # ordered write offsets: gather the counts
+            dist.all_gather_into_tensor(self.counts, self.seg_out_end[:1])
+        if ev:
+            ev[2].record()
+        self.query()
+        if ev:
+            ev[3].record()
+
+    def check_invariant(self):
+        """conservation == 1 + #{MS >= k} / membership == [1, MS >= k] over the whole shard
+        (holds for valid matching statistics; independent of the build)."""
+        torch, np = self.torch, __import__("numpy")
+        dap, off = self.dap, self.lo - self.buf_lo
+        if self.membership:
+            n_chk = min(self.Lr, 2_000_000)
+            bits = self.api.unpack_membership(self.q_out[:n_chk].cpu().numpy(), self.n_docs)
+            want = (dap[off:off + n_chk] >= self.k).cpu().numpy().astype(np.uint8)
+            assert bits[:, 0].all() and np.array_equal(bits[:, 1:], want), "membership != [1, MS >= k]"
+            return
+        step_rows = 4_000_000                            # (in slices: the comparison needs temporaries)
+        for a in range(0, self.Lr, step_rows):
+            b = min(a + step_rows, self.Lr)
+            want = (1 + (dap[off + a:off + b] >= self.k).sum(dim=1)).to(torch.uint8)
+            assert torch.equal(self.q_out[a:b], want), "query result violates conservation == 1 + #{MS >= k}"
+            del want
+
+    def owned_rows_between(self, p_lo, p_hi):
+        """Index rows (start, end, order as int64 numpy) this rank owns with p_lo <= start < p_hi."""
+        import numpy as np
+        torch = self.torch
+        n = int(self.seg_out_end[0].item())
+        f1 = self.out[0][:n]
+        a = int(torch.searchsorted(f1, torch.tensor([p_lo], dtype=torch.int32, device=self.dev)).item())
+        b = int(torch.searchsorted(f1, torch.tensor([p_hi], dtype=torch.int32, device=self.dev)).item())
+        return (self.out[0][a:b].cpu().numpy().astype(np.int64),
+                self.out[1][a:b].cpu().numpy().view(np.uint32).astype(np.int64),
+                self.out[2][a:b].cpu().numpy().astype(np.int64))
+
+
+def timed_run(wl, steps, warmup, barrier, local):
+    """W warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize."""
+    import torch
+    from memo_b200 import _lib
+    lib = _lib.load()
+    for _ in range(warmup):
+        wl.step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    lib.memo_profile_enable(1)          # CUDA events around the streaming kernel of every build
+    lib.memo_launch_count(1)
+    t_begin.record()
+    for i in range(steps):
+        wl.step(evs[i])
+    t_end.record()
+    barrier()
+    launches = int(lib.memo_launch_count(1))
+    n_out, irregular, _ = wl.builder.result()
+    assert n_out == wl.n_all and not irregular and int(wl.q_status.item()) == 0
+    lib.memo_profile_enable(0)
+    k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)
+    _lib.check(lib.memo_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)), "memo_profile_collect")
+    clocks = sampler.stop()
+    return {"total_ms": t_begin.elapsed_time(t_end),
+            "idx_ms": sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
+            "qry_ms": sum(e[2].elapsed_time(e[3]) for e in evs) / steps,
+            "kern_ms": k_ms.value / max(k_n.value, 1), "launches": launches, "clocks": clocks}
+
+
+def rooflines(wl, t, peak, peak_src, n_rows_shard, tag):
+    """Roofline objects of one rank's shard (SURVEY 8d algorithmic bytes)."""
+    C, Lr = wl.C, wl.Lr
+    bytes_idx = 4.0 * Lr * C + 12.0 * n_rows_shard       # DAP read once + index rows written once
+    ach = bytes_idx / (t["kern_ms"] * 1e-3) / 1e9
+    ach_build = bytes_idx / (t["idx_ms"] * 1e-3) / 1e9
+    bytes_q = 12.0 * wl.n_all + (4.0 * ((wl.n_docs + 31) // 32) if wl.membership else 1.0) * Lr
+    ach_q = bytes_q / (t["qry_ms"] * 1e-3) / 1e9
+    kname = "narrow_kernel" if (C <= 16) else ("wide2_kernel" if C <= 256 else "wide_kernel")
+    tr_k, src = profiled_traffic(f"{tag}_stream_kernel")
+    tr_b, _ = profiled_traffic(f"{tag}_index_build")
+    tr_q, _ = profiled_traffic(f"{tag}_query")
+    return {
+        "roofline": {"kernel": kname + " (streaming kernel of memo_index_build: DAP -> index rows; CUDA events "
+                                       "around the launch on its stream, averaged over the timed steps)",
+                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": tr_k, "traffic_source": src, "peak_source": peak_src,
+                     "algorithmic_bytes": bytes_idx, "kernel_ms": t["kern_ms"]},
+        "roofline_index_build": {"kernel": "memo_index_build (whole call)", "bound": "hbm",
+                                 "achieved": ach_build, "peak": peak, "unit": "GB/s", "frac": ach_build / peak,
+                                 "algorithmic_bytes": bytes_idx, "traffic": tr_b},
+        "roofline_query": {"kernel": "query_planes_kernel (" + ("membership" if wl.membership else "conservation") + ")",
+                           "bound": "hbm", "achieved": ach_q, "peak": peak, "unit": "GB/s", "frac": ach_q / peak,
+                           "algorithmic_bytes": bytes_q, "traffic": tr_q},
+    }
+
+
+def shard_parity(wl, args):
+    """Driver-visible multi-GPU parity: for every cut between two position shards,
+    the right-hand rank collects the index rows either side of the cut (its own first
+    `m` positions and, point to point, the left-hand rank's last `m`), and compares
+    their concatenation in rank order with the C port of the reference algorithm run
+    over the 2m positions spanning the cut; the rows' places in the ordered index
+    (exclusive prefix of the all-gathered counts) are checked on the way."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from memo_b200 import shard
+    world, rank, dev = wl.world, wl.rank, wl.dev
+    m = min(args.parity_rows, wl.rec_len // world)       # the same on every rank
+    n_local = wl.seg_out_end[:1].clone()
+    counts, offset = shard.ordered_offsets(n_local)
+    counts_h = counts.cpu().tolist()
+    ok = int(offset.item()) == sum(counts_h[:rank]) and counts_h[rank] == int(n_local.item())
+    # left-hand side of the cut at wl.hi goes to rank + 1
+    if rank + 1 < world:
+        s, e, o = wl.owned_rows_between(wl.hi - m, wl.hi)
+        t = torch.from_numpy(np.stack([s, e, o])).to(dev)
+        dist.send(torch.tensor([t.shape[1]], dtype=torch.int64, device=dev), dst=rank + 1)
+        dist.send(t.contiguous(), dst=rank + 1)
+    if rank > 0:
+        n_left = torch.zeros(1, dtype=torch.int64, device=dev)
+        dist.recv(n_left, src=rank - 1)
+        left = torch.empty((3, int(n_left.item())), dtype=torch.int64, device=dev)
+        dist.recv(left, src=rank - 1)
+        left = left.cpu().numpy()
+        cut = wl.lo
+        right = wl.owned_rows_between(cut, cut + m)
+        # the 2m positions spanning the cut, generated afresh (plus the halo row before them)
+        p0 = cut - m                              # >= 0: every shard holds at least m positions
+        h = 1 if p0 > 0 else 0
+        rows = wl.api.synth_dap(wl.rec_len, wl.C, wl.seed, row0=p0 - h, rows=2 * m + h, device=dev)
+        _, _, _, want = cpu_port_run(rows.cpu().numpy(), wl.rec_len, p0, wl.k, wl.n_docs,
+                                     min(os.cpu_count() or 1, 8), order=wl.order, halo_first=bool(h),
+                                     do_query=False)
+        sel = want[0] < cut + m                   # (chr-end rows of a shard that ends the record start at rec_len)
+        got = [np.concatenate([left[i], right[i]]) for i in range(3)]
+        ok = ok and all(np.array_equal(g, w[sel]) for g, w in zip(got, want))
+        ok = ok and int((left[0] >= cut).sum()) == 0 and (right[0].size == 0 or int(right[0].min()) >= cut)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item()), m
+
+
+def e2e_leg(wl, args, barrier):
+    """The same step through the host-buffer API (host.build_index + host.query) on a
+    host-resident slice of the shard: H2D of the DAP, D2H of rows + result inside the
+    timed wall-clock region."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from memo_b200 import api, host
+    n = min(wl.Lr, args.e2e_rows)
+    off = wl.lo - wl.buf_lo
+    sl_lo, sl_hi = wl.lo, wl.lo + n
+    halo = min(KH, wl.buf_hi - sl_hi)
+    view = wl.dap[0:off + n + halo]
+    host_dap = torch.empty(tuple(view.shape), dtype=torch.int32, pin_memory=True)
+    host_dap.copy_(view)
+    ends_record = sl_hi == wl.rec_len
+    segs = [api.Segment(row_begin=off, n_rows=n, pos0=sl_lo, rec_len=wl.rec_len, rec_id=0,
+                        flags=(api.MEMO_SEG_PRIMED if sl_lo == 0 else 0) |
+                              (api.MEMO_SEG_CHR_END if ends_record else 0))]
+    if halo:
+        segs.append(api.Segment(row_begin=off + n, n_rows=halo, pos0=sl_hi, rec_len=wl.rec_len, rec_id=0, flags=0))
+    h2d = d2h = 0
+
+    def one():
+        rows_ = host.build_index(host_dap, None, wl.order, device=wl.dev, segs=segs, raw=True, **wl.tuning)
+        q_ = host.query(rows_.start, rows_.end, rows_.order, sl_lo, sl_hi, wl.k, wl.n_docs, wl.membership,
+                        device=wl.dev, raw=True, trusted=True)
+        return rows_, q_
+
+    rows_, q_ = one()          # one untimed pass: pinned result blocks and device buffers get allocated here
+    del rows_, q_
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        rows_ = q_ = None      # drop the previous step's results (their pinned blocks recycle)
+        rows_, q_ = one()
+        h2d += host_dap.numel() * 4 + 12 * rows_.n
+        d2h += 12 * rows_.n + q_.size
+    torch.cuda.synchronize()
+    if wl.world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=wl.dev)
+    tot = torch.tensor([float(n)], dtype=torch.float64, device=wl.dev)
+    if wl.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # same rows as the device-resident path (the slice's rows are a prefix of the shard's)
+    s, e, o = wl.owned_rows_between(sl_lo, sl_hi if not ends_record else wl.rec_len + 1)
+    if not wl.membership:
+        ok = (np.array_equal(rows_.start[:s.size].astype(np.int64), s) and
+              np.array_equal(rows_.end[:s.size].astype(np.int64), e) and
+              np.array_equal(rows_.order[:s.size].astype(np.int64), o) and
+              np.array_equal(q_, wl.q_out[:n].cpu().numpy()))
+        assert ok, "host-buffer path disagrees with the device-resident path"
+    return {"value": tot.item() * args.e2e_steps / t.item(), "unit": "bp/s",
+            "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,
+            "steps": args.e2e_steps, "ms_per_step": 1e3 * t.item() / args.e2e_steps,
+            "pivot_bp_per_gpu": n,
+            "h2d_gbs_per_gpu": host_dap.numel() * 4 * args.e2e_steps / t.item() / 1e9,
+            "note": f"host.build_index + host.query on the first {n} positions of every shard: pinned host DAP "
+                    "streamed to the device in chunks overlapped with the build, index rows (12 B each) and "
+                    "the query result copied back to host; wall clock, max over ranks"}
+
+
+def cpu_leg(wl, args):
+    """C port of the reference algorithm on all host cores over a bounded sample, and
+    the GPU rows / query of the same positions compared with it."""
+    import numpy as np
+    cores = os.cpu_count() or 1
+    sample = min(wl.Lr, args.cpu_sample_rows)
+    dap_np = wl.dap[:sample].cpu().numpy()
+    dt, n_cpu, q_cpu, rows_cpu = cpu_port_run(dap_np, wl.rec_len, 0, wl.k, wl.n_docs, cores, order=wl.order)
+    got = wl.owned_rows_between(0, sample)
+    m = got[0].size
+    same = (m == int((rows_cpu[0] < sample).sum()) and
+            all(np.array_equal(g, w[:m]) for g, w in zip(got, rows_cpu)))
+    if wl.membership:
+        bits = wl.api.unpack_membership(wl.q_out[:sample - wl.k].cpu().numpy(), wl.n_docs)
+        same = same and np.array_equal(bits, q_cpu[:sample - wl.k])
     else:
-        tag = "non-default shape"
-    what = "membership index build + membership" if memb else "conservation index build +"
-    return {"workload": f"synthetic HPRC-shaped DAP, {args.cols + 1} genomes x {args.rows} bp pivot "
-                        f"per GPU ({tag}), {what} k={args.k} "
-                        "window query over the whole shard",
-            "genomes": args.cols + 1, "pivot_bp_per_gpu": args.rows, "k": args.k,
-            "partition": f"position ranges x{n_gpus}, 1-row left halo, {KH}-row right halo",
-            "l2": f"inputs ({args.rows * args.cols * 4 / 1e9:.2f} GB DAP per GPU) are larger than L2; no flush needed",
-            "seed": SEED}
+        same = same and np.array_equal(wl.q_out[:sample - wl.k].cpu().numpy(), q_cpu[:sample - wl.k])
+    return {"value": sample / dt, "unit": "bp/s", "cores": cores, "kind": "port",
+            "sample": f"first {sample} rows of the workload, one pass (index build + query); C port of the "
+                      "reference algorithm (oracle/memo_oracle.c), one slice per core",
+            "matches_gpu": bool(same), "rows_compared": int(m), "positions_compared": int(sample - wl.k)}
+
+
+def extra_config(name, rec_len, C, membership, seed, k, dev, steps, peak, peak_src, tag):
+    """A smaller BASELINE config measured after the headline one (N = 1 only): same step, plus
+    the query timed alone with L2 flushed between launches (its index rows fit in L2)."""
+    import torch
+    wl = Workload(rec_len, C, k, membership, seed, 0, 1, dev, {})
+    sync = torch.cuda.synchronize
+    t = timed_run(wl, steps, 3, sync, dev.index or 0)
+    wl.check_invariant()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    q_ms = 0.0
+    for i in range(steps + 2):
+        flush.fill_(i & 255)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        wl.query()
+        e1.record()
+        sync()
+        if i >= 2:
+            q_ms += e0.elapsed_time(e1)
+    q_ms /= steps
+    r = rooflines(wl, t, peak, peak_src, wl.n_all, tag)
+    bytes_q = r["roofline_query"]["algorithmic_bytes"]
+    return {"config": name, "genomes": C + 1, "pivot_bp": rec_len, "membership": membership,
+            "value": rec_len * steps / (t["total_ms"] * 1e-3), "unit": "bp/s",
+            "ms_per_step": t["total_ms"] / steps, "index_ms": t["idx_ms"], "query_ms": t["qry_ms"],
+            "index_rows": wl.n_all, "roofline": r["roofline"], "roofline_index_build": r["roofline_index_build"],
+            "roofline_query": r["roofline_query"],
+            "roofline_query_l2_flushed": {"query_ms": q_ms, "achieved": bytes_q / (q_ms * 1e-3) / 1e9,
+                                          "frac": bytes_q / (q_ms * 1e-3) / 1e9 / peak,
+                                          "note": "query timed alone, 512 MB written between launches"}}
 
 
 # ---------------------------------------------------------------------------
@@ -204,20 +541,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="memo_b200")
-    ap.add_argument("--rows", type=int, default=100_000_000, help="pivot bp per GPU")
-    ap.add_argument("--cols", type=int, default=9, help="DAP columns (genomes - 1)")
+    ap.add_argument("--rows", type=int, default=CHR1, help="pivot bp of the record (cut into --gpus position shards)")
+    ap.add_argument("--cols", type=int, default=93, help="DAP columns (genomes - 1)")
     ap.add_argument("--k", type=int, default=31)
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
-    ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-rows", type=int, default=16_000_000, help="host-resident slice per GPU of the e2e leg")
+    ap.add_argument("--ref-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
+    ap.add_argument("--parity-rows", type=int, default=1_000_000, help="positions either side of a shard cut compared with the port")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] / configs[2] figures")
     ap.add_argument("--rows-per-tile", type=int, default=0)
     ap.add_argument("--emit-buf", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=0, help="index kernel variant (1 = strip kernel for narrow rows)")
+    ap.add_argument("--variant", type=int, default=0, help="index kernel variant (see memo_index_opts_t)")
     ap.add_argument("--membership", action="store_true",
                     help="membership index (-m: no --order) + membership query (BASELINE configs[2])")
     ap.add_argument("--env", action="append", default=[], help="KEY=VAL set before the library loads (tuning)")
@@ -231,10 +571,9 @@ def main():
         run_reference(args)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from memo_b200 import api, host, _lib
+    from memo_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,215 +586,73 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    C, k, Lr = args.cols, args.k, args.rows
-    n_docs = C + 1
-    rec_len = Lr * world                      # one record, position-range sharded (weak scaling)
-    lo, hi = rank * Lr, (rank + 1) * Lr
-    buf_lo = lo - 1 if rank > 0 else lo       # 1-row left halo
-    buf_hi = min(hi + KH, rec_len)            # right halo for the query (rows owned by rank+1)
-    dap = api.synth_dap(rec_len, C, SEED, row0=buf_lo, rows=buf_hi - buf_lo, device=dev)
-    segs = [api.Segment(row_begin=lo - buf_lo, n_rows=Lr, pos0=lo, rec_len=rec_len, rec_id=0,
-                        flags=(api.MEMO_SEG_PRIMED if rank == 0 else 0) |
-                              (api.MEMO_SEG_CHR_END if rank == world - 1 else 0))]
-    if buf_hi > hi:
-        segs.append(api.Segment(row_begin=hi - buf_lo, n_rows=buf_hi - hi, pos0=hi, rec_len=rec_len,
-                                rec_id=0, flags=0))
-    tuning = dict(rows_per_tile=args.rows_per_tile, emit_buf_records=args.emit_buf,
-                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages,
-                  kernel_variant=args.variant)
-    builder = api.IndexBuilder(dev)
-    seg_out_end = torch.zeros(len(segs), dtype=torch.int64, device=dev)
-    # size the outputs with a counting run
-    order = not args.membership
-    builder.launch(dap, C, segs, order, None, seg_out_end, **tuning)
-    n_all, irregular, _ = builder.result()
-    assert not irregular, "synthetic DAP must be valid matching statistics"
-    out = tuple(torch.empty(n_all + 16, dtype=torch.int32, device=dev) for _ in range(3))
-    q_out = torch.empty((Lr, (n_docs + 31) // 32), dtype=torch.int32, device=dev) if args.membership \
-        else torch.empty(Lr, dtype=torch.uint8, device=dev)
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    q_status = torch.zeros(1, dtype=torch.int32, device=dev)
-    q_ws = torch.empty(max(_lib.load().memo_query_workspace_bytes(Lr), 1), dtype=torch.uint8, device=dev)
-
-    def step(ev=None):
-        # nothing in here waits for the device: the row count is known from the sizing
-        # run (and re-checked after the timed region), the query reads the fresh rows
-        if ev:
-            ev[0].record()
-        builder.launch(dap, C, segs, order, out, seg_out_end, **tuning)
-        if ev:
-            ev[1].record()
-        if world > 1:                                 # ordered write offsets: gather the counts
-            dist.all_gather_into_tensor(counts, seg_out_end[:1])
-        if ev:
-            ev[2].record()
-        if args.membership:
-            api.query_membership(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
-                                 out=q_out, check=False, status=q_status, workspace=q_ws)
-        else:
-            api.query_conservation(out[0][:n_all], out[1][:n_all], out[2][:n_all], lo, hi, k, n_docs,
-                                   out=q_out, check=False, status=q_status, workspace=q_ws)
-        if ev:
-            ev[3].record()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    t_begin = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    lib = _lib.load()
-    lib.memo_profile_enable(1)          # CUDA events around the streaming kernel of every build
-    t_begin.record()
-    for i in range(args.steps):
-        step(evs[i])
-    t_end.record()
-    barrier()
-    n_out, irregular, replays = builder.result()
-    assert n_out == n_all and not irregular and int(q_status.item()) == 0
-    lib.memo_profile_enable(0)
-    import ctypes
-    k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)
-    _lib.check(lib.memo_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)), "memo_profile_collect")
-    kern_ms = k_ms.value / max(k_n.value, 1)
-    clocks = sampler.stop()
-    total_ms = t_begin.elapsed_time(t_end)
-    idx_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    qry_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
-    n_owned = int(seg_out_end[0].item())
+    tuning = dict(rows_per_tile=args.rows_per_tile, emit_buf_records=args.emit_buf,
+                  warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages,
+                  kernel_variant=args.variant)
+    wl = Workload(args.rows, args.cols, args.k, args.membership, seed_of(args), rank, world, dev, tuning)
+    t = timed_run(wl, args.steps, args.warmup, barrier, local)
+    wl.check_invariant()                                 # correctness guard on the timed configuration
+    n_owned = int(wl.seg_out_end[0].item())
 
-    # correctness guard on the timed configuration: SURVEY 0.2 invariant
-    if args.membership:
-        # membership[p] = [1, MS_1[p] >= k, ...]: compare a slice bit by bit
-        n_chk = min(Lr, 2_000_000)
-        bits = api.unpack_membership(q_out[:n_chk].cpu().numpy(), n_docs)
-        want = (dap[lo - buf_lo:lo - buf_lo + n_chk] >= k).cpu().numpy().astype(np.uint8)
-        assert bits[:, 0].all() and np.array_equal(bits[:, 1:], want), "membership != [1, MS >= k]"
-        del bits, want
-    else:
-        step_rows = 8_000_000                        # (in slices: the comparison needs temporaries)
-        for a in range(0, Lr, step_rows):
-            b = min(a + step_rows, Lr)
-            want = (1 + (dap[lo - buf_lo + a:lo - buf_lo + b] >= k).sum(dim=1)).to(torch.uint8)
-            assert torch.equal(q_out[a:b], want), "query result violates conservation == 1 + #{MS >= k}"
-            del want
-
-    stats = torch.tensor([total_ms, idx_ms, qry_ms, float(n_owned), kern_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([t["total_ms"], t["idx_ms"], t["qry_ms"], t["kern_ms"], float(n_owned),
+                          float(t["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
-        mx = stats.clone()
+        mx, sm = stats.clone(), stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, idx_ms, qry_ms, kern_ms = mx[0].item(), mx[1].item(), mx[2].item(), mx[4].item()
-        n_owned_total = int(sm[3].item())
+        tmax = {"total_ms": mx[0].item(), "idx_ms": mx[1].item(), "qry_ms": mx[2].item(), "kern_ms": mx[3].item()}
+        n_owned_total, launches = int(sm[4].item()), int(sm[5].item())
     else:
-        n_owned_total = n_owned
+        tmax, n_owned_total, launches = t, n_owned, t["launches"]
 
-    # ---------------- end-to-end leg: host buffers through the host API
-    e2e = None
-    if not args.no_e2e and not args.membership:
-        host_dap = torch.empty(tuple(dap.shape), dtype=torch.int32, pin_memory=True)
-        host_dap.copy_(dap)
-        h2d = d2h = 0
-        # one untimed pass: pinned result blocks and device buffers get allocated here
-        rows_ = host.build_index(host_dap, None, True, device=dev, segs=segs, raw=True, **tuning)
-        q_ = host.query(rows_.start, rows_.end, rows_.order, lo, hi, k, n_docs, False, device=dev,
-                        raw=True, trusted=True)
-        del rows_, q_
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            rows_ = q_ = None                  # drop the previous step's results (their pinned blocks recycle)
-            rows_ = host.build_index(host_dap, None, True, device=dev, segs=segs, raw=True, **tuning)
-            q_ = host.query(rows_.start, rows_.end, rows_.order, lo, hi, k, n_docs, False, device=dev,
-                            raw=True, trusted=True)
-            h2d += host_dap.numel() * 4 + 12 * rows_.n
-            d2h += 12 * rows_.n + q_.size
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ok = (rows_.n == n_all and
-                  np.array_equal(rows_.start, out[0][:n_all].cpu().numpy()) and
-                  np.array_equal(rows_.end, out[1][:n_all].cpu().numpy().view(np.uint32)) and
-                  np.array_equal(rows_.order, out[2][:n_all].cpu().numpy()) and
-                  np.array_equal(q_, q_out.cpu().numpy()))
-        assert e2e_ok, "host-buffer path disagrees with the device-resident path"
-        e2e = {"value": Lr * world * args.e2e_steps / t.item(), "unit": "bp/s",
-               "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,
-               "steps": args.e2e_steps,
-               "ms_per_step": 1e3 * t.item() / args.e2e_steps,
-               "note": "host.build_index + host.query: pinned host DAP streamed to the device in 256 MB "
-                       "chunks overlapped with the build, index rows (12 B each) and the query result "
-                       "(1 B per bp) copied back to host; wall clock"}
-        del host_dap
-
-    # ---------------- CPU baseline (rank 0, N = 1 only)
+    parity = None
+    if world > 1:
+        ok, m = shard_parity(wl, args)
+        parity = {"ok": ok, "positions_each_side": m, "cuts": world - 1}
+    e2e = None if (args.no_e2e or args.membership) else e2e_leg(wl, args, barrier)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not args.membership:
-        cores = os.cpu_count() or 1
-        sample = min(Lr, args.cpu_sample_rows)
-        dap_np = dap[:sample].cpu().numpy()
-        dt, n_cpu, q_cpu, rows_cpu = cpu_port_run(dap_np, rec_len, 0, k, n_docs, cores)
-        # same sample, same answer: the GPU result must equal the CPU port's
-        m = int((out[0][:n_out] < sample).sum().item())
-        same = (np.array_equal(out[0][:m].cpu().numpy(), rows_cpu[0][:m]) and
-                np.array_equal(out[1][:m].cpu().numpy().view(np.uint32), rows_cpu[1][:m]) and
-                np.array_equal(out[2][:m].cpu().numpy(), rows_cpu[2][:m]) and
-                np.array_equal(q_out[:sample - k].cpu().numpy(), q_cpu[:sample - k]))
-        cpu = {"value": sample / dt, "unit": "bp/s", "cores": cores, "kind": "port",
-               "sample": f"first {sample} rows of the workload, one pass; C port of the reference "
-                         "algorithm (oracle/memo_oracle.c), one slice per core",
-               "matches_gpu": bool(same)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_leg(wl, args)
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # algorithmic bytes of one build: DAP read once + index rows written once
-        bytes_idx = 4.0 * Lr * C + 12.0 * n_all
-        ach = bytes_idx / (kern_ms * 1e-3) / 1e9          # dominant kernel: the streaming kernel
-        ach_build = bytes_idx / (idx_ms * 1e-3) / 1e9     # whole memo_index_build (stream + scan + gather)
-        n_q_rows = n_all
-        bytes_q = 12.0 * n_q_rows + (4.0 * ((n_docs + 31) // 32) if args.membership else 1.0) * Lr
-        ach_q = bytes_q / (qry_ms * 1e-3) / 1e9
-        value = Lr * world * args.steps / (total_ms * 1e-3)
+        tag = f"c{args.cols}_{'memb' if args.membership else 'cons'}_{wl.Lr}"
+        # max-over-ranks times against one shard's bytes (near-equal shards)
+        r = rooflines(wl, {**t, **tmax}, peak, peak_src, n_owned, tag)
+        total_ms = tmax["total_ms"]
         line = {
             "metric": "pivot bp/s (%s index build + k-mer query)" % ("membership" if args.membership else "conservation"),
-            "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(args, world),
-            "index_bp_per_s": Lr * world / (idx_ms * 1e-3),
-            "query_bp_per_s": Lr * world / (qry_ms * 1e-3),
-            "index_ms": idx_ms, "query_ms": qry_ms,
-            "index_rows": n_owned_total, "rho_cell": n_owned_total / (Lr * world * C),
-            "roofline": {"kernel": ("narrow_kernel" if C <= 16 else "wide_kernel") +
-                                   " (streaming kernel of memo_index_build: DAP -> index rows; CUDA events "
-                                   "around the launch, averaged over the timed steps)",
-                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic(C, rows=args.rows), "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_idx, "kernel_ms": kern_ms},
-            "roofline_index_build": {"kernel": "memo_index_build = streaming kernel + tile_scan + strip_gather",
-                                     "bound": "hbm", "achieved": ach_build, "peak": peak, "unit": "GB/s",
-                                     "frac": ach_build / peak, "algorithmic_bytes": bytes_idx,
-                                     "traffic": ncu_traffic(C, whole=True, rows=args.rows)},
-            "roofline_query": {"kernel": "query_stream_kernel (" + ("membership" if args.membership else "conservation") + ")", "bound": "hbm",
-                               "achieved": ach_q, "peak": peak, "unit": "GB/s", "frac": ach_q / peak,
-                               "algorithmic_bytes": bytes_q},
+            "value": args.rows * args.steps / (total_ms * 1e-3), "unit": "bp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(args, world),
+            "index_bp_per_s": args.rows / (tmax["idx_ms"] * 1e-3),
+            "query_bp_per_s": args.rows / (tmax["qry_ms"] * 1e-3),
+            "index_ms": tmax["idx_ms"], "query_ms": tmax["qry_ms"],
+            "index_rows": n_owned_total, "rho_cell": n_owned_total / (args.rows * args.cols),
+            **r,
             "cpu_baseline": cpu, "e2e": e2e,
-            # per step: index build = stream kernel + tile_scan + gather, query = one stream kernel
-            "gpu_launches": 4 * args.steps, "clocks": clocks,
+            "shard_parity": None if parity is None else parity["ok"], "shard_parity_detail": parity,
+            "gpu_launches": launches, "clocks": t["clocks"],
         }
+    del wl
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras and args.rows == CHR1 and args.cols == 93:
+        ex_steps = max(5, min(args.steps, 20))
+        line["extra_configs"] = [
+            extra_config("BASELINE configs[1]: 10 genomes x 100 Mbp, conservation", 100_000_000, 9, False,
+                         SEED0 + 1, args.k, dev, ex_steps, peak, peak_src, "c9_cons_100000000"),
+            extra_config("BASELINE configs[2]: 94 haplotypes x 5 Mbp, membership (-m)", 5_000_000, 93, True,
+                         SEED0 + 2, args.k, dev, ex_steps, peak, peak_src, "c93_memb_5000000"),
+            extra_config("94 genomes x 10 Mbp, conservation (round-1 comparison shape)", 10_000_000, 93, False,
+                         SEED0 + 3, args.k, dev, ex_steps, peak, peak_src, "c93_cons_10000000"),
+        ]
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 3
+#define MEMO_B200_ABI_VERSION 4
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -81,6 +81,11 @@ const char* memo_last_error(void);
 
 /* Number of SMs of the current device (grid sizing is in multiples of it). */
 int memo_device_sm_count(void);
+
+/* Number of kernels this library has launched in the process so far (every
+ * launch site counts); reset != 0 returns the count and clears it.  bench.py
+ * reports it as gpu_launches. */
+int64_t memo_launch_count(int32_t reset);
 
 /* Bytes of device scratch memo_index_build{,_general} need for outputs of
  * out_cap entries (the single-pass build stages its index rows there before

@@ -36,6 +36,7 @@ SIGNATURES = {
     "memo_abi_version": (C.c_int, []),
     "memo_last_error": (C.c_char_p, []),
     "memo_device_sm_count": (C.c_int, []),
+    "memo_launch_count": (_i64, [_i32]),
     "memo_index_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64, C.POINTER(Segment), _i32,
                                          C.POINTER(IndexOpts)]),
     "memo_index_build": (C.c_int, [_vp, _i64, _i32, _i32, C.POINTER(Segment), _i32,

@@ -1,6 +1,8 @@
 // Error reporting and device queries shared by the libmemo_b200.so entry points.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace memo {
@@ -13,6 +15,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int device_sm_count() {
     int dev = 0, sms = 0;
@@ -29,6 +35,10 @@ extern "C" {
 int memo_abi_version(void) { return MEMO_B200_ABI_VERSION; }
 
 const char* memo_last_error(void) { return memo::g_error; }
+
+int64_t memo_launch_count(int32_t reset) {
+    return reset ? memo::g_launches.exchange(0) : memo::g_launches.load();
+}
 
 int memo_device_sm_count(void) {
     int n = 0;

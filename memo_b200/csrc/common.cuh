@@ -31,6 +31,15 @@ void set_error(const char* fmt, ...);
         }                                    \
     } while (0)
 
+// every kernel launch of the library is counted (memo_launch_count: bench.py's gpu_launches)
+void note_launches(int n);
+
+#define MEMO_LAUNCH_CHECK(n)                 \
+    do {                                     \
+        ::memo::note_launches(n);            \
+        MEMO_CUDA_TRY(cudaGetLastError());   \
+    } while (0)
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int device_sm_count();

@@ -145,7 +145,7 @@ int memo_format_conservation(const void* vals, int32_t is_u16, int64_t n, char* 
     fmt_scan_kernel<<<1, 1024, 0, stream>>>(bs, nb, reinterpret_cast<long long*>(out_len));
     if (is_u16) fmt_write_kernel<uint16_t><<<(unsigned)nb, FT, 0, stream>>>(static_cast<const uint16_t*>(vals), n, bs, out_text);
     else fmt_write_kernel<uint8_t><<<(unsigned)nb, FT, 0, stream>>>(static_cast<const uint8_t*>(vals), n, bs, out_text);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(3);
     return MEMO_OK;
 }
 
@@ -163,7 +163,7 @@ int memo_format_membership(const uint32_t* bits, int64_t W, int32_t n_docs, char
     const long long cap = (long long)device_sm_count() * 32;
     if (grid > cap) grid = cap;
     fmt_membership_kernel<<<(unsigned)grid, 256, 0, stream>>>(bits, W, n_docs, NW, out_text);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 

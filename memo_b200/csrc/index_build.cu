@@ -529,7 +529,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         MEMO_CUDA_TRY(cudaEventRecord(ev0, stream));
     }
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     if (ev0) {
         MEMO_CUDA_TRY(cudaEventRecord(ev1, stream));
         g_profile.events.push_back(ev0);
@@ -537,7 +537,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     }
     tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_units, partial,
                                                                           done, result);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     {
         // every block of units is copied by `split` CTAs; all CTAs resident at once (8 x 256
         // threads per SM): a few CTAs left over for a second wave would double the kernel's time
@@ -549,7 +549,7 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
             seg_out_end);
     }
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 

@@ -561,7 +561,7 @@ int launch_index(const Plan& plan, IndexParams& P, bool order, cudaStream_t stre
     MEMO_CUDA_TRY(cudaMemsetAsync(P.status, 0, sizeof(unsigned long long) * (size_t)(plan.n_tickets > 0 ? plan.n_tickets : 1), stream));
     MEMO_CUDA_TRY(cudaMemsetAsync(P.ticket_counter, 0, 256, stream));
     kern<<<(unsigned)grid, threads, smem, stream>>>(P);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 
@@ -626,7 +626,7 @@ int build_common(bool general, const int32_t* dap, int64_t rows, int32_t C, int3
         carry_scan_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, stream>>>(
             P.segs, P.seg_ticket_start, n_seg, plan.NG, plan.R, C, P.agg_out, carry,
             shard_carry_in, shard_carry_out);
-        MEMO_CUDA_TRY(cudaGetLastError());
+        MEMO_LAUNCH_CHECK(1);
         P.mode = 0;
         P.carry_in = carry;
     }

@@ -223,7 +223,7 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     long long* lo = static_cast<long long*>(workspace);
     long long* hi = reinterpret_cast<long long*>(static_cast<char*>(workspace) + half);
     query_bounds_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(f1, n_rows, q_start, k, QT, n_tiles, lo, hi);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     const int sms = device_sm_count();
     long long grid = (long long)sms * (QT == 8192 ? 5 : 8);     // by shared memory / by threads
     if (grid > n_tiles) grid = n_tiles;
@@ -233,7 +233,7 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     if (out_u16) { if (QT == 8192) MEMO_QLAUNCH(uint16_t, 8192); else MEMO_QLAUNCH(uint16_t, 2048); }
     else         { if (QT == 8192) MEMO_QLAUNCH(uint8_t, 8192); else MEMO_QLAUNCH(uint8_t, 2048); }
 #undef MEMO_QLAUNCH
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 
@@ -269,7 +269,7 @@ int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* 
     if (grid > n_tiles) grid = n_tiles;
     query_membership_kernel<<<(unsigned)grid, QTHREADS, 0, stream>>>(
         f1, f2, f3, n_rows, q_start, W, k, n_docs, NW, TP, out_bits, status);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 

@@ -491,7 +491,7 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     const long long enough = (P.n_runs + QP_WARPS - 1) / QP_WARPS;
     if (grid > enough) grid = enough;
     fn<<<(unsigned)grid, QP_WARPS * 32, 0, stream>>>(P);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 

@@ -141,7 +141,7 @@ int memo_synth_dap(int32_t* dap, int64_t row0, int64_t rows, int32_t n_cols, int
     long long* chunkmax = static_cast<long long*>(workspace);
     synth_chunkmax_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_cols), SY_THREADS, 0, stream>>>(
         chunk_first, n_chunks, n_cols, rec_len, seed, dense, chunkmax);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     int sub = (int)((200 * 1024 / sizeof(long long) - n_cols) / n_cols);
     if (sub > SY_SUB_MAX) sub = SY_SUB_MAX;
     MEMO_REQUIRE(sub >= 1, "n_cols too large for the generator");
@@ -149,7 +149,7 @@ int memo_synth_dap(int32_t* dap, int64_t row0, int64_t rows, int32_t n_cols, int
     MEMO_CUDA_TRY(cudaFuncSetAttribute(synth_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     synth_fill_kernel<<<(unsigned)(c_hi - c_lo + 1), SY_THREADS, smem, stream>>>(
         dap, row0, rows, n_cols, ld, rec_len, seed, dense, chunk_first, chunkmax, sub);
-    MEMO_CUDA_TRY(cudaGetLastError());
+    MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
 }
 

@@ -33,8 +33,10 @@ def read_dap_text(path) -> Tuple[int, np.ndarray]:
     if table.num_columns < 2:
         raise MemoError("dap.txt needs a position column and at least one genome column")
     for i, col in enumerate(table.columns):
-        if not pa.types.is_integer(col.type):
-            raise ValueError(f"invalid literal for int() in DAP column {i}")     # int() in the reference
+        if not pa.types.is_integer(col.type) or col.null_count:
+            # int() in the reference (an empty field -- double space, ragged `paste` output --
+            # parses as null here and raises there: src/dap_to_bed.py:87)
+            raise ValueError(f"invalid literal for int() in DAP column {i}")
     L = table.num_rows
     if L == 0:
         return 0, np.zeros((0, table.num_columns - 1), dtype=np.int32)

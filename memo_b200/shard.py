@@ -73,12 +73,16 @@ def plan_shard(records: Sequence[Tuple[str, int]], total_rows: int, world: int, 
     buf_lo = lo - 1 if needs_halo else lo
     buf_hi = min(hi + halo_right, total_rows)
     owned = _runs(records, lo, hi, buf_lo, first_continues=needs_halo)
-    # a run that continues on the next rank leaves its chr-end rows to that rank
+    # a run that continues on the next rank leaves its chr-end rows to that rank; the run that
+    # ends the DAP always emits them, also when the DAP stops inside the record
+    # (src/dap_to_bed.py:133-134 runs after the last row whatever the record's .fai length)
     if owned and hi < total_rows:
         last = owned[-1]
         rec_end = sum(l for _, l in records[:last.rec_id + 1])
         if hi < rec_end:
             last.flags &= ~MEMO_SEG_CHR_END
+    elif owned:
+        owned[-1].flags |= MEMO_SEG_CHR_END
     halo = _runs(records, hi, buf_hi, buf_lo, first_continues=True) if buf_hi > hi else []
     for s in halo:
         s.flags &= ~MEMO_SEG_CHR_END            # halo rows only feed this rank's queries

@@ -27,6 +27,9 @@ def load():
         _lib.mo_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(Seg),
                                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64]
+        _lib.mo_synth_dap.restype = None
+        _lib.mo_synth_dap.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
+                                      C.c_uint64, C.c_int32]
         _lib.mo_query.restype = C.c_int
         _lib.mo_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -78,4 +81,24 @@ def query(f1, f2, f3, q_start, q_end, k, n_docs, membership):
                       n_docs, int(membership), out.ctypes.data)
     if rc != 0:
         raise IndexError("index row order/genome id out of range for -n")
+    return out
+
+
+def synth_dap(rec_len, n_cols, seed, row0=0, rows=None, dense=False, threads=1):
+    """Rows [row0, row0+rows) of the synthetic DAP (same integers as
+    memo_oracle.synth_dap), `threads` row slices generated in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = load()
+    rows = rec_len - row0 if rows is None else rows
+    out = np.empty((rows, n_cols), dtype=np.int32)
+    threads = max(1, min(threads, rows // 65536 or 1))
+    cuts = [(rows * i) // threads for i in range(threads + 1)]
+
+    def work(i):
+        a, b = cuts[i], cuts[i + 1]
+        if b > a:
+            lib.mo_synth_dap(out[a:b].ctypes.data, row0 + a, b - a, n_cols, rec_len, seed, int(dense))
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
     return out

@@ -135,3 +135,50 @@ int mo_query(const int64_t* f1, const int64_t* f2, const int64_t* f3, int64_t n_
     free(rec);
     return 0;
 }
+
+/* Synthetic HPRC-shaped DAP (measurement input; same integers as
+ * oracle/memo_oracle.py:synth_dap, which tests/test_oracle_c.py checks): rows
+ * [row0, row0 + rows) of one record of length rec_len into dap[rows, C].
+ *   h = splitmix64(seed ^ p*K1 ^ c*K2); short draw 12 + ctz(h | 2^20); with
+ *   probability 2^-9 a long draw ((ctz((h>>32) | 2^16) + 1) << 10) + ((h>>48) & 1023);
+ *   MS[p][c] = min(max_{q<=p}(d[q][c] + q) - p, rec_len - p). */
+static inline uint64_t mo_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+void mo_synth_dap(int32_t* dap, int64_t row0, int64_t rows, int32_t C, int64_t rec_len,
+                  uint64_t seed, int32_t dense) {
+    const int64_t LOOKBACK = 32768;                 /* draws are < 2^15 */
+    const int64_t lo = row0 > LOOKBACK ? row0 - LOOKBACK : 0;
+    int64_t* reach = malloc(sizeof(int64_t) * C);
+    for (int c = 0; c < C; ++c) reach[c] = 0;
+    for (int64_t p = lo; p < row0 + rows; ++p) {
+        const uint64_t pp = (uint64_t)p * 0x9E3779B97F4A7C15ull;
+        int32_t* out = p >= row0 ? dap + (p - row0) * (int64_t)C : NULL;
+        for (int c = 0; c < C; ++c) {
+            const uint64_t h = mo_splitmix64(seed ^ pp ^ ((uint64_t)c * 0xC2B2AE3D27D4EB4Full));
+            int64_t d = 12 + __builtin_ctzll(h | (1ull << 20));
+            if (dense) {
+                if (((h >> 20) & 1023) == 0) {
+                    const int64_t dl = (((int64_t)__builtin_ctzll((h >> 32) | (1ull << 16)) + 1) << 8) +
+                                       (int64_t)((h >> 48) & 255);
+                    if (dl > d) d = dl;
+                }
+            } else if (((h >> 20) & 511) == 0) {
+                const int64_t dl = (((int64_t)__builtin_ctzll((h >> 32) | (1ull << 16)) + 1) << 10) +
+                                   (int64_t)((h >> 48) & 1023);
+                if (dl > d) d = dl;
+            }
+            if (d + p > reach[c]) reach[c] = d + p;
+            if (out) {
+                int64_t ms = reach[c] - p;
+                if (ms > rec_len - p) ms = rec_len - p;
+                out[c] = (int32_t)ms;
+            }
+        }
+    }
+    free(reach);
+}

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in memo_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.memo_abi_version() == 3
+    assert lib.memo_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
@@ -233,3 +233,37 @@ def test_query_rows_for_range_on_oracle():
                 a, b = shard.query_rows_for_range(s, lo, hi, max(ks))
                 parts.append(mo.query(s[a:b], e[a:b], c[a:b], lo, hi, k, C + 1, False))
             assert np.array_equal(np.concatenate(parts), whole), (world, k)
+
+
+def test_sharded_build_partial_dap_keeps_chr_end_rows():
+    """A DAP that stops inside the last record still gets that record's chr-end rows
+    (src/dap_to_bed.py:133-134 runs after the last row whatever the .fai length)."""
+    from memo_b200 import shard
+    from oracle import c_oracle as co
+    recs = [("a", 100), ("b", 50)]
+    C = 4
+    vals = np.concatenate([mo.synth_dap(100, C, seed=1, dense=True), mo.synth_dap(50, C, seed=2, dense=True)[:20]])
+    whole = co.index_build(vals, recs, True)
+    assert (whole[1] == 50).any()
+    for world in (1, 2, 3):
+        parts = []
+        for rank in range(world):
+            p = shard.plan_shard(recs, len(vals), world, rank)
+            segs = [co.Seg(s.row_begin, s.n_rows, s.pos0, s.rec_len, s.rec_id, s.flags)
+                    for s in p.segs[:p.n_owned]]
+            parts.append(co.index_build(vals[p.buf_lo:p.buf_hi], recs, True, segs=segs))
+        for j in range(4):
+            assert np.array_equal(np.concatenate([q[j] for q in parts]), whole[j]), world
+
+
+def test_dap_text_empty_field_raises_like_int(tmp_path):
+    """An empty field (double space / ragged `paste` output) is int('') in the reference
+    (src/dap_to_bed.py:87): ValueError, not a silent INT32_MIN."""
+    from memo_b200 import io
+    p = tmp_path / "dap.txt"
+    p.write_text("0 3 5\n1  5\n2 4 4\n")
+    with pytest.raises(ValueError):
+        io.read_dap_text(str(p))
+    p.write_text("0 3 5\n1 2 \n2 4 4\n")
+    with pytest.raises(ValueError):
+        io.read_dap_text(str(p))

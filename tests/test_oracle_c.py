@@ -62,3 +62,14 @@ def test_c_oracle_halo_slices_match_for_valid_ms():
         parts.append(co.index_build(vals[lo:b], recs, True, segs=segs))
     for j in range(4):
         assert np.array_equal(np.concatenate([p[j] for p in parts]), whole[j])
+
+
+def test_c_synth_matches_numpy_synth():
+    """bench.py's reference arm generates its sample with the C generator."""
+    for dense in (False, True):
+        a = mo.synth_dap(3_000_000, 7, 99, row0=123_456, rows=70_000, dense=dense)
+        b = co.synth_dap(3_000_000, 7, 99, row0=123_456, rows=70_000, dense=dense)
+        assert np.array_equal(a, b)
+        a = mo.synth_dap(200_000, 5, 3, dense=dense)
+        b = co.synth_dap(200_000, 5, 3, dense=dense, threads=3)
+        assert np.array_equal(a, b)
