@@ -64,7 +64,9 @@ typedef struct memo_index_opts {
     int32_t warps_per_cta;    /* 0 = default (8) */
     int32_t ctas_per_sm;      /* cap on resident CTAs per SM, 0 = as many as fit */
     int32_t stages;           /* bulk-copy pipeline depth per warp, 0 = default (2), max 4 */
-    int32_t kernel_variant;   /* 0 = pick, 1 = force the strip kernel for narrow rows too (tests) */
+    int32_t kernel_variant;   /* 0 = pick, 1 = strip kernel for narrow rows too (tests), 2 = the
+                                 two-pass strip kernel (scratch + gather) instead of the
+                                 single-kernel strip build */
     int32_t reserved;
 } memo_index_opts_t;
 

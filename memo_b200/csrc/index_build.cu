@@ -48,6 +48,7 @@ struct Profile {
     std::vector<cudaEvent_t> events;
 };
 thread_local Profile g_profile;
+int pick_build(int32_t C, int32_t ld, const memo_index_opts_t* opts);
 
 // ---------------------------------------------------------------- scan
 // partial[b] = index rows of tile block b; the last block to arrive turns
@@ -398,7 +399,39 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     return MEMO_OK;
 }
 
+// which build a shape takes: 0 = lane-per-row tiles (narrow rows), 1 = the single-kernel
+// strip build (index_wide2.cu), 2 = the strip kernel with scratch + gather (index_wide.cu:
+// rows wider than 256 columns, or kernel_variant 2)
+int pick_build(int32_t C, int32_t ld, const memo_index_opts_t* opts) {
+    const int variant = opts ? opts->kernel_variant : 0;
+    const bool narrow = ld == C && variant == 0 && select_narrow_kernel(C, true, nullptr) != nullptr;
+    if (narrow) return 0;
+    if (variant != 2 && wide2_supported(C, ld)) return 1;
+    return 2;
+}
+
 }  // namespace
+
+void profile_begin(cudaStream_t stream) {
+    if (!g_profile.on) return;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, stream);
+    g_profile.events.push_back(ev);
+}
+
+void profile_end(cudaStream_t stream) {
+    if (!g_profile.on || (g_profile.events.size() & 1) == 0) return;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) {
+        cudaEventDestroy(g_profile.events.back());
+        g_profile.events.pop_back();
+        return;
+    }
+    cudaEventRecord(ev, stream);
+    g_profile.events.push_back(ev);
+}
+
 }  // namespace memo
 
 extern "C" {
@@ -434,7 +467,12 @@ size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int6
         return 0;
     const size_t general = memo::general_workspace_bytes(rows, n_cols, segs, n_seg, opts);
     if (general == 0) return 0;
-    return plan.total > general ? plan.total : general;
+    size_t fast = plan.total;
+    if (memo::pick_build(n_cols, ld, opts) == 1) {
+        fast = memo::wide2_workspace_bytes(rows, n_cols, ld, segs, n_seg, opts);
+        if (fast == 0) return 0;
+    }
+    return fast > general ? fast : general;
 }
 
 int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld,
@@ -450,6 +488,10 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     MEMO_REQUIRE(out_cap == 0 || (out_start && out_end && out_order), "out_* NULL with out_cap > 0");
     MEMO_REQUIRE((reinterpret_cast<uintptr_t>(dap) & 15) == 0, "dap must be 16-byte aligned");
     MEMO_REQUIRE(n_seg == 0 || seg_out_end != nullptr, "seg_out_end must not be NULL");
+    MEMO_REQUIRE(n_cols >= 1 && out_cap >= 0, "bad n_cols / out_cap");
+    if (pick_build(n_cols, ld, opts) == 1)
+        return launch_wide2(dap, rows, n_cols, ld, segs, n_seg, opts, out_start, out_end, out_order, out_cap,
+                            seg_out_end, result, workspace, workspace_bytes, stream);
     FastPlan plan;
     long long* tstart = new long long[(size_t)n_seg + 1];
     int rc = make_fast_plan(rows, n_cols, ld, out_cap, segs, n_seg, opts, &plan, tstart);
@@ -522,19 +564,10 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, 256, stream));
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (g_profile.on) {
-        MEMO_CUDA_TRY(cudaEventCreate(&ev0));
-        MEMO_CUDA_TRY(cudaEventCreate(&ev1));
-        MEMO_CUDA_TRY(cudaEventRecord(ev0, stream));
-    }
+    profile_begin(stream);
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     MEMO_LAUNCH_CHECK(1);
-    if (ev0) {
-        MEMO_CUDA_TRY(cudaEventRecord(ev1, stream));
-        g_profile.events.push_back(ev0);
-        g_profile.events.push_back(ev1);
-    }
+    profile_end(stream);
     tile_scan_kernel<<<(unsigned)plan.n_blocks, SCAN_THREADS, 0, stream>>>(P.tile_cnt, plan.n_units, partial,
                                                                           done, result);
     MEMO_LAUNCH_CHECK(1);

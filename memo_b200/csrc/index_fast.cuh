@@ -194,6 +194,20 @@ typedef void (*stream_kernel_t)(const FastParams);
 // positions per lane.
 stream_kernel_t select_wide_kernel(int n_cols, bool order, int* kpl);
 
+// index_wide2.cu: the single-kernel strip build (TMA tensor staging, phase A row scan,
+// decoupled look-back straight into the ordered output) for rows of up to 256 columns
+bool wide2_supported(int32_t n_cols, int32_t ld);
+size_t wide2_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, const memo_segment_t* segs,
+                             int32_t n_seg, const memo_index_opts_t* opts);
+int launch_wide2(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld, const memo_segment_t* segs,
+                 int32_t n_seg, const memo_index_opts_t* opts, int32_t* out_start, uint32_t* out_end,
+                 int32_t* out_order, int64_t out_cap, int64_t* seg_out_end, int64_t* result,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// index_build.cu: CUDA events around the streaming kernel while memo_profile_enable is on
+void profile_begin(cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+
 // index_narrow.cu: kernel for n_cols == ld == CT (compile-time) rows, or nullptr.
 // *rows_per_lane receives the number of consecutive rows a lane scans per step
 // (tile bases must be multiples of it so that they are 16-byte aligned).
