@@ -330,6 +330,7 @@ def timed_run(wl, steps, warmup, barrier, local):
     launches = int(lib.memo_launch_count(1))
     n_out, irregular, _ = wl.builder.result()
     assert n_out == wl.n_all and not irregular and int(wl.q_status.item()) == 0
+    parked = int(wl.builder._result[3].item())           # (stat of the single-kernel strip build)
     lib.memo_profile_enable(0)
     k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)
     _lib.check(lib.memo_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)), "memo_profile_collect")
@@ -337,7 +338,8 @@ def timed_run(wl, steps, warmup, barrier, local):
     return {"total_ms": t_begin.elapsed_time(t_end),
             "idx_ms": sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
             "qry_ms": sum(e[2].elapsed_time(e[3]) for e in evs) / steps,
-            "kern_ms": k_ms.value / max(k_n.value, 1), "launches": launches, "clocks": clocks}
+            "kern_ms": k_ms.value / max(k_n.value, 1), "launches": launches, "clocks": clocks,
+            "parked_rows": parked}
 
 
 def rooflines(wl, t, peak, peak_src, n_rows_shard, tag):
@@ -348,7 +350,7 @@ def rooflines(wl, t, peak, peak_src, n_rows_shard, tag):
     ach_build = bytes_idx / (t["idx_ms"] * 1e-3) / 1e9
     bytes_q = 12.0 * wl.n_all + (4.0 * ((wl.n_docs + 31) // 32) if wl.membership else 1.0) * Lr
     ach_q = bytes_q / (t["qry_ms"] * 1e-3) / 1e9
-    kname = "narrow_kernel" if (C <= 16) else ("wide2_kernel" if C <= 256 else "wide_kernel")
+    kname = "wide2_kernel" if wl.tuning.get("kernel_variant") == 3 else ("narrow_kernel" if C <= 16 else "wide_kernel")
     tr_k, src = profiled_traffic(f"{tag}_stream_kernel")
     tr_b, _ = profiled_traffic(f"{tag}_index_build")
     tr_q, _ = profiled_traffic(f"{tag}_query")
@@ -635,6 +637,7 @@ def main():
             "query_bp_per_s": args.rows / (tmax["qry_ms"] * 1e-3),
             "index_ms": tmax["idx_ms"], "query_ms": tmax["qry_ms"],
             "index_rows": n_owned_total, "rho_cell": n_owned_total / (args.rows * args.cols),
+            "index_rows_parked_rank0": t["parked_rows"],
             **r,
             "cpu_baseline": cpu, "e2e": e2e,
             "shard_parity": None if parity is None else parity["ok"], "shard_parity_detail": parity,

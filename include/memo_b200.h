@@ -64,9 +64,9 @@ typedef struct memo_index_opts {
     int32_t warps_per_cta;    /* 0 = default (8) */
     int32_t ctas_per_sm;      /* cap on resident CTAs per SM, 0 = as many as fit */
     int32_t stages;           /* bulk-copy pipeline depth per warp, 0 = default (2), max 4 */
-    int32_t kernel_variant;   /* 0 = pick, 1 = strip kernel for narrow rows too (tests), 2 = the
-                                 two-pass strip kernel (scratch + gather) instead of the
-                                 single-kernel strip build */
+    int32_t kernel_variant;   /* 0 = pick, 1 = strip kernel for narrow rows too (tests), 3 = the
+                                 single-kernel strip build (ordered in-place writes through a
+                                 look-back over strips; any width) */
     int32_t reserved;
 } memo_index_opts_t;
 
@@ -76,6 +76,8 @@ typedef struct memo_index_opts {
                                 the fast build's output must be discarded and
                                 memo_index_build_general run instead */
 #define MEMO_RES_REPLAYS 2   /* general build: strips whose staging buffer overflowed (stat) */
+#define MEMO_RES_PARKED 3    /* single-kernel strip build: index rows that went through the parking
+                                area because an earlier strip was still running (stat) */
 #define MEMO_RES_SLOTS 4
 
 int memo_abi_version(void);

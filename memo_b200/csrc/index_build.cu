@@ -399,15 +399,14 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     return MEMO_OK;
 }
 
-// which build a shape takes: 0 = lane-per-row tiles (narrow rows), 1 = the single-kernel
-// strip build (index_wide2.cu), 2 = the strip kernel with scratch + gather (index_wide.cu:
-// rows wider than 256 columns, or kernel_variant 2)
+// which build a shape takes: 0 = lane-per-row tiles (narrow rows), 2 = the strip kernel with
+// scratch + gather (index_wide.cu), 1 = the single-kernel strip build (index_wide2.cu: ordered
+// in-place writes; measured slower on B200 -- DESIGN.md 4.3 -- so only on request: kernel_variant 3)
 int pick_build(int32_t C, int32_t ld, const memo_index_opts_t* opts) {
     const int variant = opts ? opts->kernel_variant : 0;
+    if (variant == 3 && wide2_supported(C, ld)) return 1;
     const bool narrow = ld == C && variant == 0 && select_narrow_kernel(C, true, nullptr) != nullptr;
-    if (narrow) return 0;
-    if (variant != 2 && wide2_supported(C, ld)) return 1;
-    return 2;
+    return narrow ? 0 : 2;
 }
 
 }  // namespace
@@ -469,7 +468,7 @@ size_t memo_index_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int6
     if (general == 0) return 0;
     size_t fast = plan.total;
     if (memo::pick_build(n_cols, ld, opts) == 1) {
-        fast = memo::wide2_workspace_bytes(rows, n_cols, ld, segs, n_seg, opts);
+        fast = memo::wide2_workspace_bytes(rows, n_cols, ld, out_cap, segs, n_seg, opts);
         if (fast == 0) return 0;
     }
     return fast > general ? fast : general;

@@ -197,7 +197,7 @@ stream_kernel_t select_wide_kernel(int n_cols, bool order, int* kpl);
 // index_wide2.cu: the single-kernel strip build (TMA tensor staging, phase A row scan,
 // decoupled look-back straight into the ordered output) for rows of up to 256 columns
 bool wide2_supported(int32_t n_cols, int32_t ld);
-size_t wide2_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, const memo_segment_t* segs,
+size_t wide2_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int64_t out_cap, const memo_segment_t* segs,
                              int32_t n_seg, const memo_index_opts_t* opts);
 int launch_wide2(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld, const memo_segment_t* segs,
                  int32_t n_seg, const memo_index_opts_t* opts, int32_t* out_start, uint32_t* out_end,

@@ -30,13 +30,23 @@
 //            a delete/insert (positions holding x <= A <= y shift by one), the
 //            positions where A changed are the row's index rows.  A is sorted from
 //            scratch once per strip (warp bitonic merge-split network).
-// Index rows are staged in the warp's shared memory (16-byte records; a dense
-// strip spills to a per-warp global overflow area).  When its strip ends the warp
-// publishes the strip's row count, obtains the sum over all earlier strips by a
-// decoupled look-back (status word per strip: aggregate / inclusive prefix) and
-// copies the staged rows to out_* with coalesced stores: no scratch round trip, no
-// scan or gather kernel.  Strips are handed out in order by an atomic counter, so a
-// strip's predecessors are always running or done: the look-back cannot deadlock.
+// Index rows are staged in the warp's shared memory (8-byte records {end, row | order};
+// a dense strip spills to a per-warp global overflow area) and written straight to
+// their place in the ordered output: no scratch round trip, no scan or gather kernel.
+// The place of a strip = rows of all earlier strips, resolved on two levels (a chain
+// over 2 M strips, 32 per L2 round trip, would be slower than the build itself):
+//   * a strip publishes its row count when its rows are through (status word) and counts
+//     itself into its group of 32 consecutive strips; the group's last finisher sums the
+//     group, looks back over the earlier GROUPS (aggregate / inclusive prefix per group,
+//     decoupled look-back) and publishes the group's inclusive prefix;
+//   * a strip's offset = inclusive prefix of the previous group + counts of the earlier
+//     strips of its own group.
+// The staging area is double buffered: a strip is resolved and copied out (coalesced
+// stores) after the warp's NEXT strip is through, when its predecessors have normally
+// long finished.  No warp ever waits: a strip whose predecessors are still running by
+// then (behind a dense stretch of the DAP) is PARKED -- its staged records go to a
+// global parking area -- and wide2_finish_kernel, which also writes the per-run row
+// totals, copies the parked strips to their places afterwards.
 #include <mutex>
 #include <vector>
 
@@ -49,6 +59,9 @@ namespace {
 constexpr int W2_WARPS = 4;            // warps per CTA (independent streams)
 constexpr int W2_INLINE_SEGS = 8;      // record runs passed in the kernel parameters
 constexpr int W2_MAX_T = 28;           // rows per chunk (row flags of a chunk + the rows around it: 32 bits)
+constexpr int W2_MAX_WORDS = 3968;     // words per chunk (phase A: one flag bit per 128 words)
+constexpr int W2_CTAS = 5;             // CTAs per SM the shared-memory budget is cut for
+constexpr int W2_FIFO = 16;            // finished strips a warp can keep waiting in its ring
 
 struct Wide2Params {
     const int32_t* dap;
@@ -63,11 +76,19 @@ struct Wide2Params {
     memo_segment_t isegs[W2_INLINE_SEGS];
     long long iunit[W2_INLINE_SEGS + 1];
     long long n_units;
-    uint32_t warp_smem, off_stage, off_stg, off_bar;   // bytes inside the warp's region
+    uint32_t warp_smem, off_stage, off_stg, off_bar, off_fifo;   // bytes inside the warp's region
     uint32_t cap;                      // staged index rows per warp (shared memory)
-    unsigned long long* status;        // [n_units] (value << 2) | {0 none, 1 aggregate, 2 inclusive}
+    uint2* ring;                       // per-warp ring of finished strips' records (global, L2 resident)
+    uint32_t ring_cap;                 // records per warp, a power of two
+    unsigned long long* status;        // [n_units] (rows of the strip << 1) | 1 once published
+    unsigned int* gdone;               // [n_groups] published strips of the group
+    unsigned long long* gstatus;       // [n_groups] (value << 2) | {0 none, 1 group total, 2 inclusive prefix}
     unsigned long long* strip_counter;
-    uint4* ovf;                        // per-warp overflow of the staging area
+    unsigned long long* park_cursor;   // next free record of the parking area
+    unsigned long long* park_off;      // [n_units] 1 + first parked record of the strip, 0 = written in place
+    uint2* park;                       // parking area
+    long long park_cap;
+    uint2* ovf;                        // per-warp overflow of the staging area
     long long ovf_cap;
     int32_t* out_start;
     uint32_t* out_end;
@@ -86,8 +107,12 @@ template <int SHIFT>
 __device__ __forceinline__ uint32_t scan_chunk(const uint32_t* st, int off, int n, int ld, uint32_t magic, int lane) {
     const int n_quads = (off + n * ld + 3) >> 2;
     const int back = (ld + 3) >> 2;                              // quads back to the first needed word's quad
-    uint32_t bits = 0;
-    for (int q = lane; q < n_quads; q += 32) {
+    // pass 1, branch free: bit (32 - iterations + i) of `hit` = the lane's quad of iteration i
+    // holds a changed cell
+    uint32_t hit = 0;
+    int iters = 0;
+#pragma unroll 4
+    for (int q = lane; q < n_quads; q += 32, ++iters) {
         const uint4 c = *reinterpret_cast<const uint4*>(st + 4 * q);
         uint32_t p0, p1, p2, p3;
         if (SHIFT == 0) {
@@ -101,25 +126,110 @@ __device__ __forceinline__ uint32_t scan_chunk(const uint32_t* st, int off, int 
             else { p0 = a.y; p1 = a.z; p2 = a.w; p3 = b.x; }
         }
         const uint32_t d = (c.x + 1u - p0) | (c.y + 1u - p1) | (c.z + 1u - p2) | (c.w + 1u - p3);
-        if (d != 0u) {
-            // words 4q .. 4q+3 of the stage = words u .. u+3 counted from the start of the row
-            // before the chunk; they belong to row u / ld and (a quad across a row end) (u+3) / ld
-            const uint32_t u = (uint32_t)(4 * q - off + ld);
-            if (ld >= 3) {
-                bits |= (1u << __umulhi(u, magic)) | (1u << __umulhi(u + 3u, magic));
-            } else {
-                // one- and two-column rows: a quad spans up to four rows (and 2^32 / 1 does not
-                // fit the multiplier)
+        hit = __funnelshift_r(hit, min(d, 1u), 1);
+    }
+    // pass 2 (few lanes, few quads): the rows of the flagged quads.  Words 4q .. 4q+3 of the
+    // stage = words u .. u+3 counted from the start of the row before the chunk; they belong
+    // to row u / ld and (a quad across a row end) (u+3) / ld
+    uint32_t bits = 0;
+    const int first_bit = 32 - iters;
+    while (hit) {
+        const int b = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const uint32_t u = (uint32_t)(4 * (lane + 32 * (b - first_bit)) - off + ld);
+        if (ld >= 3) {
+            bits |= (1u << __umulhi(u, magic)) | (1u << __umulhi(u + 3u, magic));
+        } else {
+            // one- and two-column rows: a quad spans up to four rows (and 2^32 / 1 does not
+            // fit the multiplier)
 #pragma unroll
-                for (uint32_t i = 0; i < 4u; ++i) bits |= 1u << ((u + i) >> (ld - 1));
-            }
+            for (uint32_t i = 0; i < 4u; ++i) bits |= 1u << ((u + i) >> (ld - 1));
         }
     }
     return __reduce_or_sync(FULL, bits);
 }
 
+__device__ __forceinline__ long long w2_unit_start(const Wide2Params& P, int i) {
+    return P.n_seg <= W2_INLINE_SEGS ? P.iunit[i] : P.seg_unit_start[i];
+}
+// record run of strip s (binary search over the runs' first strips)
+__device__ __forceinline__ int w2_find_run(const Wide2Params& P, long long s) {
+    int a = 0, b = P.n_seg - 1;
+    while (a < b) {
+        const int mid = (a + b + 1) >> 1;
+        if (w2_unit_start(P, mid) <= s) a = mid; else b = mid - 1;
+    }
+    return a;
+}
+
+// Rows of all strips before strip s: inclusive prefix of the previous group + the earlier
+// strips of the strip's own group.  Never waits: returns false when a strip or group it needs
+// is not published yet.  The group prefix is materialised lazily: whoever needs it walks back
+// over the group totals to the nearest inclusive prefix (32 groups per step) and leaves the
+// result behind for the others.
+__device__ __forceinline__ bool w2_resolve(const Wide2Params& P, long long s, int lane, unsigned long long* excl) {
+    volatile unsigned long long* const st = P.status;
+    volatile unsigned long long* const gs = P.gstatus;
+    const long long g = s >> 5;
+    const int k = (int)(s & 31);
+    unsigned long long v = 0;
+    bool ok = true;
+    if (lane < k) {
+        const unsigned long long w = st[(g << 5) + lane];
+        ok = (w & 1ull) != 0ull;
+        v = w >> 1;
+    }
+    if (!__all_sync(FULL, ok)) return false;
+    if (g > 0) {
+        long long idx = g - 1;
+        bool first = true;
+        unsigned long long base = 0;
+        for (;;) {
+            const long long j = idx - lane;
+            const unsigned long long w = j >= 0 ? gs[j] : 2ull;          // before the first group: inclusive 0
+            const unsigned inc = __ballot_sync(FULL, (w & 3ull) == 2ull);
+            const unsigned none = __ballot_sync(FULL, (w & 3ull) == 0ull);
+            const int f = inc ? __ffs(inc) - 1 : 31;                     // walk ends at the nearest inclusive prefix
+            if (none & (0xFFFFFFFFu >> (31 - f))) return false;          // a group on the way is not complete
+            unsigned long long t = lane <= f ? (w >> 2) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+            base += t;
+            if (inc) {
+                if (!(first && f == 0) && lane == 0) gs[g - 1] = (base << 2) | 2ull;
+                break;
+            }
+            first = false;
+            idx -= 32;
+        }
+        if (lane == 0) v += base;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    *excl = v;
+    return true;
+}
+
+// n staged records -> out_* at `excl`; p0 = position of the strip's first compare row, plen =
+// its record's length (chr-end rows); records [0, ns) from sb, the rest from ob
+__device__ __forceinline__ void w2_copy_out(const Wide2Params& P, const uint2* sb, const uint2* ob, uint32_t ns,
+                                            unsigned long long excl, uint32_t total, uint32_t p0, uint32_t plen,
+                                            int lane) {
+    const unsigned long long ocap = (unsigned long long)P.out_cap;
+    for (uint32_t i = lane; i < total; i += 32) {
+        const uint2 e = i < ns ? sb[i] : ob[i - ns];
+        const unsigned long long gi = excl + i;
+        if (gi < ocap) {
+            const uint32_t rc = e.y >> 16;
+            P.out_start[gi] = (int32_t)(rc == 0xFFFFu ? plen : p0 + rc);
+            P.out_end[gi] = e.x;
+            P.out_order[gi] = (int32_t)(e.y & 0xFFFFu);
+        }
+    }
+}
+
 template <int KPL, bool ORDER>
-__global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Params P) {
+__global__ void __launch_bounds__(W2_WARPS * 32, W2_CTAS) wide2_kernel(const Wide2Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -129,10 +239,16 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
 
     unsigned char* const wbase = smem_raw + (size_t)warp * P.warp_smem;
     uint32_t* const stage = reinterpret_cast<uint32_t*>(wbase + P.off_stage);    // (ld + 4 words of room in front)
-    uint4* const stg = reinterpret_cast<uint4*>(wbase + P.off_stg);
+    uint2* const stg = reinterpret_cast<uint2*>(wbase + P.off_stg);              // staged records of the strip
     uint64_t* const bar = reinterpret_cast<uint64_t*>(wbase + P.off_bar);
+    uint4* const fifo = reinterpret_cast<uint4*>(wbase + P.off_fifo);            // W2_FIFO x {s lo, s hi, total, p0} {plen, start, -, -}
     const uint32_t cap = P.cap;
-    uint4* const ovf = P.ovf + ((long long)blockIdx.x * W2_WARPS + warp) * P.ovf_cap;
+    const long long gwarp = (long long)blockIdx.x * W2_WARPS + warp;
+    uint2* const ovf = P.ovf + gwarp * P.ovf_cap;
+    uint2* const ring = P.ring + gwarp * (long long)P.ring_cap;
+    const uint32_t ring_mask = P.ring_cap - 1u;
+    uint32_t ring_head = 0, ring_tail = 0;       // records appended / retired so far
+    uint32_t fifo_head = 0, fifo_n = 0;          // strips pushed so far / waiting
     const unsigned char* const src_bytes = reinterpret_cast<const unsigned char*>(P.dap);
 
     // phase B: slot k of lane l is DAP column l + 32 k (only the last slot can lie past the
@@ -163,20 +279,12 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
     int off = 0;                                 // word offset of the chunk's first row inside the stage
     uint32_t parity = 0, irr = 0;
 
-    auto unit_start = [&](int i) -> long long {
-        return P.n_seg <= W2_INLINE_SEGS ? P.iunit[i] : P.seg_unit_start[i];
-    };
     auto locate = [&](long long s) {
         if (s < c_lo || s >= c_hi) {
-            int a = 0, b = P.n_seg - 1;
-            while (a < b) {
-                const int mid = (a + b + 1) >> 1;
-                if (unit_start(mid) <= s) a = mid; else b = mid - 1;
-            }
-            run = a;
-            c_lo = unit_start(a);
-            c_hi = unit_start(a + 1);
-            seg = P.n_seg <= W2_INLINE_SEGS ? P.isegs[a] : P.segs[a];
+            run = w2_find_run(P, s);
+            c_lo = w2_unit_start(P, run);
+            c_hi = w2_unit_start(P, run + 1);
+            seg = P.n_seg <= W2_INLINE_SEGS ? P.isegs[run] : P.segs[run];
         }
         const long long primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
         const long long fc = seg.row_begin + primed;             // first compare row of the run
@@ -219,9 +327,13 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
     for (int k = 0; k < KPL; ++k) A[k] = 0;
     uint32_t n_emit = 0;               // index rows of the strip so far
 
-    // index rows of one DAP row: em[k] / endv[k] per slot, `p` = BED start.  Output order:
-    // ORDER -> position ibase + k; else column lane + 32 k.
-    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t p) {
+    uint32_t ordk[KPL];                // BED f3 of the slot: ORDER -> position ibase + k; else column lane + 32 k
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) ordk[k] = (uint32_t)(ORDER ? ibase + k : lane + 32 * k) + 1u;
+    // index rows of one DAP row: em[k] / endv[k] per slot; rowcode = the row's offset from the
+    // strip's first compare row (0xFFFF: chr-end rows), from which the copy-out rebuilds the BED
+    // start.  Output order = f3 ascending.
+    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t rowcode) {
         unsigned b[KPL];
         uint32_t total = 0, rank = 0;
 #pragma unroll
@@ -234,22 +346,32 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
 #pragma unroll
             for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
         }
-        const uint32_t base = n_emit;
+        const uint32_t rc = rowcode << 16;
+        rank += n_emit;
         n_emit += total;
-        const bool fits = base + total <= cap;                        // warp uniform
+        if (n_emit <= cap) {                                          // warp uniform: the usual case
 #pragma unroll
-        for (int k = 0; k < KPL; ++k) {
-            const uint32_t rk = base + (ORDER ? rank : rank + __popc(b[k] & ltmask));
-            if (em[k]) {
-                const uint4 rec = make_uint4(p, endv[k], (uint32_t)(ORDER ? ibase + k : lane + 32 * k) + 1u, 0u);
-                if (fits || rk < cap) stg[rk] = rec; else ovf[rk - cap] = rec;
+            for (int k = 0; k < KPL; ++k) {
+                const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
+                if (em[k]) stg[rk] = make_uint2(endv[k], rc | ordk[k]);
+                if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
             }
-            if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
+                if (em[k]) {
+                    const uint2 rec = make_uint2(endv[k], rc | ordk[k]);
+                    if (rk < cap) stg[rk] = rec; else ovf[rk - cap] = rec;
+                }
+                if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
+            }
         }
     };
 
     // one flagged row: rp = its raw values (the row before: ld words back), pos = its position
     auto process_row = [&](const uint32_t* rp, uint32_t pos) {
+        const uint32_t rowcode = pos - pos_r0;
         const uint32_t* pp = rp - ld;
         uint32_t prev[KPL], dk[KPL], acc = 0;
 #pragma unroll
@@ -341,55 +463,92 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
                 endv[k] = e;
             }
         }
-        emit(em, endv, pos);
+        emit(em, endv, rowcode);
     };
 
-    // sum over all earlier strips (decoupled look-back); publishes this strip's inclusive prefix
-    auto lookback = [&](long long s, unsigned long long total) -> unsigned long long {
-        unsigned long long excl = 0;
-        volatile unsigned long long* const st = P.status;
-        if (s > 0) {
-            if (lane == 0) st[s] = (total << 2) | 1ull;
-            long long idx = s - 1;
-            for (;;) {
-                const long long j = idx - lane;
-                unsigned long long w = 2ull;                          // before the first strip: inclusive 0
-                if (j >= 0) {
-                    do { w = st[j]; } while ((w & 3ull) == 0ull);
-                }
-                const unsigned inc = __ballot_sync(FULL, (w & 3ull) == 2ull);
-                unsigned long long v = w >> 2;
-                if (inc != 0u && lane > __ffs(inc) - 1) v = 0;        // stop at the nearest inclusive prefix
+    volatile unsigned long long* const st = P.status;
+    volatile unsigned long long* const gs = P.gstatus;
+    // the strip's rows are through: publish its count; the last finisher of a group of 32
+    // strips publishes the group's total (nobody waits for anybody)
+    auto publish = [&](long long s, unsigned long long total) {
+        const long long g = s >> 5;
+        unsigned old = 0;
+        if (lane == 0) {
+            st[s] = (total << 1) | 1ull;
+            __threadfence();
+            old = atomicAdd(&P.gdone[g], 1u);
+        }
+        old = __shfl_sync(FULL, old, 0);
+        const long long g_first = g << 5;
+        const int g_size = (int)min(32ll, P.n_units - g_first);
+        if ((int)old != g_size - 1) return;
+        __threadfence();
+        unsigned long long gt = lane < g_size ? (st[g_first + lane] >> 1) : 0ull;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                excl += v;
-                if (inc != 0u) break;
-                idx -= 32;
-            }
-        }
-        if (lane == 0) st[s] = ((excl + total) << 2) | 2ull;
-        return excl;
+        for (int o = 16; o > 0; o >>= 1) gt += __shfl_xor_sync(FULL, gt, o);
+        if (lane == 0) gs[g] = (gt << 2) | (g == 0 ? 2ull : 1ull);
     };
-    auto flush = [&](unsigned long long excl, uint32_t total) {
-        __syncwarp();
+    // strips of this warp whose rows wait in its ring, oldest first: copied to their place once
+    // every earlier strip is published
+    auto drain = [&](bool blocking) {
         const unsigned long long ocap = (unsigned long long)P.out_cap;
-        const uint32_t ns = total < cap ? total : cap;
-        for (uint32_t i = lane; i < ns; i += 32) {
-            const uint4 e = stg[i];
-            const unsigned long long gi = excl + i;
-            if (gi < ocap) {
-                P.out_start[gi] = (int32_t)e.x;
-                P.out_end[gi] = e.y;
-                P.out_order[gi] = (int32_t)e.z;
+        while (fifo_n) {
+            const uint32_t slot = (fifo_head - fifo_n) & (W2_FIFO - 1);
+            const uint4 m0 = fifo[2 * slot], m1 = fifo[2 * slot + 1];
+            const long long ps = (long long)(((unsigned long long)m0.y << 32) | m0.x);
+            unsigned long long excl = 0;
+            if (!w2_resolve(P, ps, lane, &excl)) {
+                if (!blocking) break;
+                __nanosleep(500);
+                continue;
             }
+            const uint32_t total = m0.z, p0 = m0.w, plen = m1.x, start = m1.y;
+            for (uint32_t i = lane; i < total; i += 32) {
+                const uint2 e = ring[(start + i) & ring_mask];
+                const unsigned long long gi = excl + i;
+                if (gi < ocap) {
+                    const uint32_t rcd = e.y >> 16;
+                    P.out_start[gi] = (int32_t)(rcd == 0xFFFFu ? plen : p0 + rcd);
+                    P.out_end[gi] = e.x;
+                    P.out_order[gi] = (int32_t)(e.y & 0xFFFFu);
+                }
+            }
+            ring_tail = start + total;
+            --fifo_n;
         }
-        for (uint32_t i = cap + lane; i < total; i += 32) {
-            const uint4 e = ovf[i - cap];
-            const unsigned long long gi = excl + i;
-            if (gi < ocap) {
-                P.out_start[gi] = (int32_t)e.x;
-                P.out_end[gi] = e.y;
-                P.out_order[gi] = (int32_t)e.z;
+    };
+    // a finished strip (records in the staging area): straight to its place if nothing of this
+    // warp waits and every earlier strip is published; else into the warp's ring; a strip that
+    // does not fit the ring is parked for wide2_finish_kernel.  Nothing waits for anything.
+    auto place = [&](long long ps, uint32_t total, uint32_t p0, uint32_t plen) {
+        __syncwarp();
+        drain(false);
+        if (P.out_cap == 0) return;                                   // counting run: nothing to keep
+        const uint32_t ns = total < cap ? total : cap;
+        unsigned long long excl = 0;
+        if (fifo_n == 0 && w2_resolve(P, ps, lane, &excl)) {
+            w2_copy_out(P, stg, ovf, ns, excl, total, p0, plen, lane);
+        } else if (fifo_n < W2_FIFO && total <= P.ring_cap - (ring_head - ring_tail)) {
+            for (uint32_t i = lane; i < total; i += 32) ring[(ring_head + i) & ring_mask] = i < ns ? stg[i] : ovf[i - ns];
+            if (lane == 0) {
+                const uint32_t slot = fifo_head & (W2_FIFO - 1);
+                fifo[2 * slot] = make_uint4((uint32_t)ps, (uint32_t)((unsigned long long)ps >> 32), total, p0);
+                fifo[2 * slot + 1] = make_uint4(plen, ring_head, 0u, 0u);
+            }
+            ring_head += total;
+            ++fifo_head;
+            ++fifo_n;
+        } else {
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(P.park_cursor, (unsigned long long)total);
+            at = __shfl_sync(FULL, at, 0);
+            if (at + total <= (unsigned long long)P.park_cap) {
+                for (uint32_t i = lane; i < total; i += 32) P.park[at + i] = i < ns ? stg[i] : ovf[i - ns];
+                if (lane == 0) P.park_off[ps] = at + 1ull;
+            } else {
+                // (parking area full: cannot happen with park_cap = out_cap; wait as a last resort)
+                while (!w2_resolve(P, ps, lane, &excl)) __nanosleep(500);
+                w2_copy_out(P, stg, ovf, ns, excl, total, p0, plen, lane);
             }
         }
         __syncwarp();
@@ -403,11 +562,15 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
         locate(s);
         // first chunk: the strip's predecessor row + up to T - 1 compare rows
         issue_rows(r0 - 1, min((long long)T, r1 - r0 + 1));
-        if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);      // one strip ahead: hides the atomic
     }
     const int shift = ld & 3;
     while (s < P.n_units) {
         // ---- the strip's rows
+        bool claimed = false;
+        if (r1 - (r0 - 1) <= T) {                    // a single chunk: the next strip is claimed now
+            if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
+            claimed = true;
+        }
         mbar_wait(bar, parity);
         parity ^= 1u;
         if (ORDER) {
@@ -459,6 +622,13 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
             }
             __syncwarp();                                            // the stage is free again
             issue_rows(cur, n_next);
+            if (!claimed && cur + n_next >= r1) {
+                // the strip's last chunk: claim the next strip now -- late, so that few strips are
+                // claimed but not started (the strips after them would have to be parked), early
+                // enough to hide the atomic
+                if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
+                claimed = true;
+            }
             mbar_wait(bar, parity);
             parity ^= 1u;
         }
@@ -473,28 +643,61 @@ __global__ void __launch_bounds__(W2_WARPS * 32, 4) wide2_kernel(const Wide2Para
                 em[k] = valid && e >= rec_len;
                 endv[k] = min(e, 2u * rec_len);
             }
-            emit(em, endv, rec_len);
+            emit(em, endv, 0xFFFFu);
         }
-        // ---- next strip's first load goes out before this strip's rows are published
+        // ---- publish the strip's count and place its rows; the next strip's first load goes out
+        //      before either
         const long long fin_s = s;
-        const uint32_t fin_total = n_emit;
-        const bool fin_last = s_last;
-        const int fin_run = run;
+        const uint32_t fin_total = n_emit, fin_p0 = pos_r0, fin_len = rec_len;
         __syncwarp();                                                // the stage is free
         s = (long long)__shfl_sync(FULL, look, 0);
         if (s < P.n_units) {
             locate(s);
             issue_rows(r0 - 1, min((long long)T, r1 - r0 + 1));
-            if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
         }
-        const unsigned long long excl = lookback(fin_s, fin_total);
-        flush(excl, fin_total);
+        publish(fin_s, fin_total);
+        place(fin_s, fin_total, fin_p0, fin_len);
+    }
+    drain(true);
+    if (irr >> 31) P.result[MEMO_RES_IRREGULAR] = 1;
+}
+
+// After the strip kernel: rows up to the end of every record run (seg_out_end), the grand
+// total, and the parked strips to their places.  Every count is published by now.
+__global__ void __launch_bounds__(256) wide2_finish_kernel(const Wide2Params P) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i <= P.n_seg; i += n_warps) {
+        const long long last = (i < P.n_seg ? w2_unit_start(P, (int)i + 1) : P.n_units) - 1;   // i == n_seg: everything
+        unsigned long long excl = 0;
+        w2_resolve(P, last, lane, &excl);
+        const unsigned long long incl = excl + (P.status[last] >> 1);
         if (lane == 0) {
-            if (fin_last) P.seg_out_end[fin_run] = (int64_t)(excl + fin_total);
-            if (fin_s + 1 == P.n_units) P.result[MEMO_RES_N_OUT] = (int64_t)(excl + fin_total);
+            if (i < P.n_seg) P.seg_out_end[i] = (int64_t)incl; else P.result[MEMO_RES_N_OUT] = (int64_t)incl;
         }
     }
-    if (irr >> 31) P.result[MEMO_RES_IRREGULAR] = 1;
+    if (warp == 0 && lane == 0) P.result[3] = (int64_t)*P.park_cursor;      // (stat: index rows that were parked)
+    if (P.out_cap == 0) return;
+    for (long long s0 = warp * 32; s0 < P.n_units; s0 += n_warps * 32) {
+        const unsigned long long po = s0 + lane < P.n_units ? P.park_off[s0 + lane] : 0ull;
+        unsigned m = __ballot_sync(FULL, po != 0ull);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const long long s = s0 + src;
+            const unsigned long long at = __shfl_sync(FULL, po, src) - 1ull;
+            const int run = w2_find_run(P, s);
+            const memo_segment_t seg = P.n_seg <= W2_INLINE_SEGS ? P.isegs[run] : P.segs[run];
+            const long long fc = seg.row_begin + ((seg.flags & MEMO_SEG_PRIMED) ? 1 : 0);
+            const long long r0 = fc + (s - w2_unit_start(P, run)) * (long long)P.R;
+            const uint32_t p0 = (uint32_t)seg.pos0 + (uint32_t)(r0 - seg.row_begin);
+            const uint32_t total = (uint32_t)(P.status[s] >> 1);
+            unsigned long long excl = 0;
+            w2_resolve(P, s, lane, &excl);
+            w2_copy_out(P, P.park + at, P.park + at, total, excl, total, p0, (uint32_t)seg.rec_len, lane);
+        }
+    }
 }
 
 typedef void (*wide2_kernel_t)(const Wide2Params);
@@ -510,10 +713,11 @@ wide2_kernel_t select_wide2(int kpl, bool order) {
 
 struct Wide2Plan {
     int kpl, T, R;
-    uint32_t off_stage, off_stg, off_bar, warp_smem, cap;
+    uint32_t off_stage, off_stg, off_bar, off_fifo, warp_smem, cap, ring_cap;
     size_t smem;
     long long n_units, grid_warps, ovf_cap;
-    size_t off_segs, off_ustart, off_status, off_ctrl, off_ovf, total;
+    long long park_cap;
+    size_t off_segs, off_ustart, off_status, off_gdone, off_gstatus, off_parkoff, off_ctrl, off_ovf, off_ring, off_park, total;
 };
 
 // resident CTAs per SM of a kernel variant on a device for a dynamic shared-memory size.  The
@@ -543,38 +747,40 @@ int wide2_ctas_per_sm(wide2_kernel_t kern, size_t smem) {
     return n;
 }
 
-int make_wide2_plan(int64_t rows, int32_t C, int32_t ld, const memo_segment_t* segs, int32_t n_seg,
+int make_wide2_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const memo_segment_t* segs, int32_t n_seg,
                     const memo_index_opts_t* opts, Wide2Plan* plan, long long* ustart) {
     plan->kpl = (C + 31) / 32;
     const long long row_bytes = (long long)ld * 4;
-    // shared memory of one warp, four CTAs of W2_WARPS warps per SM (227 KB - 1 KB per CTA):
-    //   room for the row before the chunk | stage: T rows (+ alignment slack, + what phase A / B
-    //   read past the last row) | barrier | staged index rows
-    const long long per_warp = ((227 * 1024) / 4 - 1024) / W2_WARPS / 128 * 128;
+    // shared memory of one warp, W2_CTAS CTAs of W2_WARPS warps per SM (227 KB - 1 KB per CTA):
+    //   room for the row before the chunk | stage: T rows (+ alignment slack, + what phase B
+    //   reads past the last row) | barrier | table of waiting strips | staged index rows (8 B each)
+    const long long per_warp = ((227 * 1024) / W2_CTAS - 1024) / W2_WARPS / 128 * 128;
     const long long front = (long long)align_up((size_t)row_bytes + 16, 128);
     const long long over = 144;                                   // phase B reads up to 31 words past a row
-    const long long fixed = front + 32 + over + 16;
-    // ~70 % of the warp's share for DAP rows, the rest for staged index rows
-    long long t = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : (per_warp * 11 / 16 - fixed) / row_bytes;
+    const long long fixed = front + 32 + over + 16 + 32 * W2_FIFO;
+    // ~65 % of the warp's share for DAP rows, the rest for staged index rows
+    long long t = (opts && opts->rows_per_tile > 0) ? opts->rows_per_tile : (per_warp * 21 / 32 - fixed) / row_bytes;
     if (t > W2_MAX_T) t = W2_MAX_T;
-    while (t > 2 && fixed + t * row_bytes + 16 * 64 > 55 * 1024) --t;     // (very wide rows: one CTA per SM)
+    while (t > 2 && (fixed + t * row_bytes + 16 * 64 > 55 * 1024 || t * ld > W2_MAX_WORDS)) --t;   // (very wide rows)
     if (t < 2) t = 2;
     plan->T = (int)t;
     // about 128 rows per strip, a whole number of chunks (the predecessor row is one of them)
     long long r = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records
                                                        : (128 / t > 1 ? 128 / t : 1) * t - 1;
     if (r < 1) r = 1;
+    if (r > 60000) r = 60000;                                     // (16-bit row codes in the staged records)
     plan->R = (int)r;
     size_t o = (size_t)front;
     plan->off_stage = (uint32_t)o;  o = align_up(o + (size_t)(t * row_bytes) + 32 + (size_t)over, 16);
     plan->off_bar = (uint32_t)o;    o += 16;
+    plan->off_fifo = (uint32_t)o;   o += 32 * W2_FIFO;
     plan->off_stg = (uint32_t)o;
-    long long cap = (long long)o + 16 * 64 <= per_warp ? (per_warp - (long long)o) / 16 : 64;
-    if (cap > 1024) cap = 1024;
+    long long cap = (long long)o + 8 * 64 <= per_warp ? (per_warp - (long long)o) / 8 : 64;
+    if (cap > 2048) cap = 2048;
     cap = cap / 32 * 32;
     if (cap < 32) cap = 32;
     plan->cap = (uint32_t)cap;
-    plan->warp_smem = (uint32_t)align_up(o + 16 * (size_t)cap, 128);
+    plan->warp_smem = (uint32_t)align_up(o + 8 * (size_t)cap, 128);
     plan->smem = (size_t)plan->warp_smem * W2_WARPS;
     MEMO_REQUIRE(plan->smem <= 227 * 1024, "strip configuration needs %zu B of shared memory", plan->smem);
 
@@ -597,7 +803,7 @@ int make_wide2_plan(int64_t rows, int32_t C, int32_t ld, const memo_segment_t* s
     }
     if (ustart) ustart[n_seg] = u;
     plan->n_units = u;
-    const long long sm_warps = (long long)device_sm_count() * 4 * W2_WARPS;
+    const long long sm_warps = (long long)device_sm_count() * W2_CTAS * W2_WARPS;
     const long long unit_warps = (u + W2_WARPS - 1) / W2_WARPS * W2_WARPS;
     plan->grid_warps = unit_warps < sm_warps ? unit_warps : sm_warps;
     // a strip emits at most (rows of the strip + 1) * C index rows
@@ -607,8 +813,18 @@ int make_wide2_plan(int64_t rows, int32_t C, int32_t ld, const memo_segment_t* s
     plan->off_segs = off;    off = align_up(off + sizeof(memo_segment_t) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
     plan->off_ustart = off;  off = align_up(off + sizeof(long long) * (size_t)(n_seg + 1), 256);
     plan->off_ctrl = off;    off = align_up(off + 256, 256);
+    const size_t ng = (size_t)((u + 31) / 32 + 1);
     plan->off_status = off;  off = align_up(off + 8 * (size_t)(u > 0 ? u : 1), 256);
-    plan->off_ovf = off;     off = align_up(off + 16 * (size_t)plan->ovf_cap * (size_t)plan->grid_warps, 256);
+    plan->off_gdone = off;   off = align_up(off + 4 * ng, 256);
+    plan->off_gstatus = off; off = align_up(off + 8 * ng, 256);
+    plan->off_parkoff = off; off = align_up(off + 8 * (size_t)(u > 0 ? u : 1), 256);
+    plan->off_ovf = off;     off = align_up(off + 8 * (size_t)plan->ovf_cap * (size_t)plan->grid_warps, 256);
+    // ring of a warp: ~10 average strips (it stays in L2: written and read back within microseconds)
+    plan->ring_cap = 2048;
+    plan->off_ring = off;    off = align_up(off + 8 * (size_t)plan->ring_cap * (size_t)plan->grid_warps, 256);
+    // parking area: strips whose predecessors were late (at most every index row once)
+    plan->park_cap = out_cap;
+    plan->off_park = off;    off = align_up(off + 8 * (size_t)plan->park_cap + 256, 256);
     plan->total = off;
     return MEMO_OK;
 }
@@ -619,10 +835,10 @@ bool wide2_supported(int32_t n_cols, int32_t ld) {
     return n_cols >= 1 && n_cols <= 512 && ld >= n_cols && ld <= 2 * n_cols + 8;
 }
 
-size_t wide2_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, const memo_segment_t* segs,
+size_t wide2_workspace_bytes(int64_t rows, int32_t n_cols, int32_t ld, int64_t out_cap, const memo_segment_t* segs,
                              int32_t n_seg, const memo_index_opts_t* opts) {
     Wide2Plan plan;
-    if (make_wide2_plan(rows, n_cols, ld, segs, n_seg, opts, &plan, nullptr) != MEMO_OK) return 0;
+    if (make_wide2_plan(rows, n_cols, ld, out_cap, segs, n_seg, opts, &plan, nullptr) != MEMO_OK) return 0;
     return plan.total;
 }
 
@@ -632,7 +848,7 @@ int launch_wide2(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld, c
                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     Wide2Plan plan;
     std::vector<long long> ustart((size_t)n_seg + 1);
-    int rc = make_wide2_plan(rows, n_cols, ld, segs, n_seg, opts, &plan, ustart.data());
+    int rc = make_wide2_plan(rows, n_cols, ld, out_cap, segs, n_seg, opts, &plan, ustart.data());
     if (rc != MEMO_OK) return rc;
     if (workspace_bytes < plan.total || workspace == nullptr) {
         set_error("workspace too small: %zu < %zu", workspace_bytes, plan.total);
@@ -668,10 +884,18 @@ int launch_wide2(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld, c
         P.seg_unit_start = reinterpret_cast<const long long*>(ws + plan.off_ustart);
     }
     P.warp_smem = plan.warp_smem; P.off_stage = plan.off_stage;
-    P.off_stg = plan.off_stg; P.off_bar = plan.off_bar; P.cap = plan.cap;
+    P.off_stg = plan.off_stg; P.off_bar = plan.off_bar; P.off_fifo = plan.off_fifo; P.cap = plan.cap;
+    P.ring = reinterpret_cast<uint2*>(ws + plan.off_ring);
+    P.ring_cap = plan.ring_cap;
     P.strip_counter = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl);
+    P.park_cursor = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl + 128);
+    P.park_off = reinterpret_cast<unsigned long long*>(ws + plan.off_parkoff);
+    P.park = reinterpret_cast<uint2*>(ws + plan.off_park);
+    P.park_cap = plan.park_cap;
     P.status = reinterpret_cast<unsigned long long*>(ws + plan.off_status);
-    P.ovf = reinterpret_cast<uint4*>(ws + plan.off_ovf);
+    P.gdone = reinterpret_cast<unsigned int*>(ws + plan.off_gdone);
+    P.gstatus = reinterpret_cast<unsigned long long*>(ws + plan.off_gstatus);
+    P.ovf = reinterpret_cast<uint2*>(ws + plan.off_ovf);
     P.ovf_cap = plan.ovf_cap;
     P.out_start = out_start; P.out_end = out_end; P.out_order = out_order; P.out_cap = out_cap;
     P.seg_out_end = seg_out_end; P.result = result;
@@ -682,17 +906,26 @@ int launch_wide2(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t ld, c
         return MEMO_ERR_UNSUPPORTED;
     }
     if (opts && opts->ctas_per_sm > 0 && opts->ctas_per_sm < per_sm) per_sm = opts->ctas_per_sm;
-    if (per_sm > 4) per_sm = 4;                                   // (the overflow area is sized for 4)
+    if (per_sm > W2_CTAS) per_sm = W2_CTAS;                       // (the per-warp areas are sized for that many)
     long long grid = (long long)device_sm_count() * per_sm;
     const long long need = (plan.n_units + W2_WARPS - 1) / W2_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    // strip counter + status words of all strips
+    // strip counter, parking cursor, status words of all strips, group counters and status words,
+    // parking table
     MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, plan.off_ovf - plan.off_ctrl, stream));
     profile_begin(stream);
     kern<<<(unsigned)grid, W2_WARPS * 32, plan.smem, stream>>>(P);
     MEMO_LAUNCH_CHECK(1);
     profile_end(stream);
+    {
+        long long fgrid = (plan.n_units + 32 * 8 - 1) / (32 * 8);
+        const long long fmax = (long long)device_sm_count() * 4;
+        if (fgrid > fmax) fgrid = fmax;
+        if (fgrid < 1) fgrid = 1;
+        wide2_finish_kernel<<<(unsigned)fgrid, 256, 0, stream>>>(P);
+        MEMO_LAUNCH_CHECK(1);
+    }
     return MEMO_OK;
 }
 

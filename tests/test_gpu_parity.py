@@ -137,6 +137,12 @@ def test_index_valid_ms_all_geometries(C, order):
     # tiny strips / tiny staging buffers: exercises look-back and the replay path
     res, got = gpu_index(vals[:3000], [("chrS", 3000)], order, rows_per_tile=8, emit_buf_records=4)
     assert_index_equal(got, mo.index_build(vals[:3000], [("chrS", 3000)], order), f"C={C} tiny")
+    # the single-kernel strip build (index_wide2.cu: ordered in-place writes), default and tiny shapes
+    res, got = gpu_index(vals, recs, order, kernel_variant=3)
+    assert_index_equal(got, want, f"C={C} order={order} single-kernel")
+    assert not res.irregular and not res.general
+    res, got = gpu_index(vals[:3000], [("chrS", 3000)], order, kernel_variant=3, rows_per_tile=8, emit_buf_records=4)
+    assert_index_equal(got, mo.index_build(vals[:3000], [("chrS", 3000)], order), f"C={C} single-kernel tiny")
 
 
 @pytest.mark.parametrize("C", [3, 9, 20, 40, 93, 150])
@@ -181,7 +187,8 @@ def test_index_narrow_kernel_shapes(C, order):
                            for i, n in enumerate(lens)])
     want = mo.index_build(vals, recs, order)
     for kw in ({}, {"rows_per_tile": 1}, {"rows_per_tile": 512}, {"rows_per_tile": 900, "stages": 1, "warps_per_cta": 4},
-               {"stages": 4, "warps_per_cta": 3}, {"kernel_variant": 1}):
+               {"stages": 4, "warps_per_cta": 3}, {"kernel_variant": 1}, {"kernel_variant": 3},
+               {"kernel_variant": 3, "rows_per_tile": 5, "emit_buf_records": 7}):
         res, got = gpu_index(vals, recs, order, **kw)
         assert_index_equal(got, want, f"narrow C={C} order={order} {kw}")
         assert not res.general
