@@ -53,7 +53,26 @@ def check_args(args):
         raise Exception("Error: Can only print overlaps if printing MEMs.")
 
 
+def dap_blocks(args):
+    """(first position, iterator of int32 [n, C] blocks of consecutive DAP rows): the input is
+    streamed like the reference streams it (src/dap_to_bed.py:14-18), never held as a whole."""
+    from . import io
+    if args.lengths_paths is not None:
+        return 0, io.iter_lengths_columns(args.lengths_paths)
+    it = io.iter_dap_text(args.dap_path)
+    first = next(it, None)
+    if first is None:
+        return 0, iter(())
+
+    def blocks():
+        yield first[1]
+        for _, block in it:
+            yield block
+    return first[0], blocks()
+
+
 def main(args, sink=None):
+    import pyarrow as pa
     from . import api, host, io
     if args.print_ms:
         # dead code in the reference too (NameError at src/dap_to_bed.py:51)
@@ -61,14 +80,19 @@ def main(args, sink=None):
     if not args.print_overlaps:
         raise NotImplementedError("only `--mem --overlap` (what `memo index` runs) is on the device path")
     records = api.parse_fai(args.fai_path)
-    if args.lengths_paths is not None:
-        pos0, dap = 0, io.read_lengths_columns(args.lengths_paths)
-    else:
-        pos0, dap = io.read_dap_text(args.dap_path)
-    if dap.shape[0] == 0:
+    names = pa.array([r[0] for r in records], type=pa.utf8())
+    sink = sys.stdout.buffer if sink is None else sink
+
+    def on_rows(rec_counts, start, end, order):          # BED rows of one chunk, in print order
+        io.write_bed(io.index_batch(names, rec_counts, start, end, order), sink)
+
+    pos0, blocks = dap_blocks(args)
+    chunk_bytes = int(os.environ.get("MEMO_CHUNK_BYTES", host.DEFAULT_CHUNK_BYTES))
+    stats = {}
+    host.build_index_streaming(blocks, records, args.sort_lcps, on_rows, pos_first=pos0,
+                               chunk_bytes=chunk_bytes, stats=stats)
+    if not stats:
         raise KeyError(None)          # reference: fai_dict[None] after an empty DAP
-    rec, start, end, col = host.build_index(dap, records, args.sort_lcps, pos_first=pos0)
-    io.write_bed(io.index_table(records, rec, start, end, col), sink)
 
 
 if __name__ == "__main__":

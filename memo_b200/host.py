@@ -116,6 +116,285 @@ class IndexRowsHost:
                 self.order.astype(np.int64))
 
 
+class IndexStream:
+    """Streaming DAP -> index rows with O(chunk) memory, the shape of the reference's row loop
+    (src/dap_to_bed.py:14-18,116-134: one pass, rows in, BED rows out).
+
+    feed() takes blocks of consecutive DAP rows (int32 [n, C], any sizes); they are packed into
+    a ring of pinned chunks (each carries the row before it as its halo), copied to the device
+    on a copy stream while the previous chunk builds, and the index rows of every chunk come
+    back through `on_rows(rec_counts, start, end, order)` in the reference's print order
+    (rec_counts = [(record index, rows)], start / end / order = int32 / uint32 / int32 numpy
+    views that are only valid during the call).  A chunk is submitted when the row after it
+    arrives (or at finish()): whether its last run gets chr-end rows depends on that.
+
+    Input that is not valid matching statistics: from the first chunk the device flags, the
+    stream switches to the exact three-pass build, chunk by chunk, with the per-column carry
+    handed from chunk to chunk (everything before that chunk was regular, for which the single-
+    pass rows are exact and the carry is the sorted MEM ends of the halo row)."""
+
+    def __init__(self, records: Optional[Sequence[Tuple[str, int]]], order: bool, n_cols: int, on_rows,
+                 device=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES, pos_first: int = 0,
+                 segs_all: Optional[List[api.Segment]] = None, on_device: bool = False, **tuning):
+        """segs_all: explicit record runs over the rows fed (row 0 = the first row fed), e.g. a
+        position shard with halo rows, instead of the records / pos_first layout of index.sh:83.
+        on_device: on_rows receives a DEVICE tensor int32 [3, n] (valid until the stream's main
+        CUDA stream has run RING - 1 more chunks) instead of host views."""
+        self.records, self.order, self.C, self.on_rows, self.tuning = list(records or []), order, n_cols, on_rows, tuning
+        self.segs_all, self.on_device = segs_all, on_device
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.builder = api.IndexBuilder(self.dev)
+        C = n_cols
+        self.chunk_rows = max(1, chunk_bytes // (4 * C))
+        self.cap = max(1024, int(self.chunk_rows * C * 0.025) + 2 * C)
+        self.main = torch.cuda.current_stream(self.dev)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.back_stream = torch.cuda.Stream(self.dev)
+        self.slots = []                     # allocated on demand (a short input needs one)
+        self.k = 0                          # chunks submitted so far
+        self.collected = 0                  # chunks handed to on_rows so far
+        self.fill = 0                       # rows waiting in the current slot
+        self.pos = pos_first                # global position of the next row to arrive
+        self.pos_stream0 = pos_first
+        self.starts, acc = set(), 0
+        for _, length in self.records:
+            self.starts.add(acc)
+            acc += length
+        self.src = None                     # rows of the current chunk taken in place (pinned caller memory)
+        self.last_row = None                # last row fed so far
+        self.prev_last_row = None           # last row of the chunk submitted before the current one
+        self.general = False                # exact build from here on (irregular input seen)
+        self.carry = None                   # device int64 [C]: per-column end of the last flagged MEM
+        self.n_out = 0
+        self.n_chunks_general = 0
+
+    # ---- buffers
+    def _slot(self, i):
+        while len(self.slots) <= i % RING:
+            C, n = self.C, self.chunk_rows + 1
+            self.slots.append({
+                "pin": None,                # pinned staging of the chunk's rows (allocated when a block needs it)
+                "pin_halo": torch.empty((1, C), dtype=torch.int32, pin_memory=True),
+                "dev": torch.empty((n, C), dtype=torch.int32, device=self.dev),      # row 0 = halo row
+                "out": torch.empty((3, self.cap), dtype=torch.int32, device=self.dev),
+                "pin_out": None if self.on_device else torch.empty((3, self.cap), dtype=torch.int32, pin_memory=True),
+                "res": torch.zeros(RES_SLOTS, dtype=torch.int64, device=self.dev),
+                "pin_res": torch.zeros(RES_SLOTS, dtype=torch.int64, pin_memory=True),
+            })
+        return self.slots[i % RING]
+
+    def _fill_slot(self, i):
+        """Slot of chunk i, its pinned input free to be written (the copy of the chunk that used
+        the slot before has left it)."""
+        slot = self._slot(i)
+        ev = slot.pop("h2d", None)
+        if ev is not None:
+            ev.synchronize()
+        return slot
+
+    def feed(self, block) -> None:
+        """Rows [pos, pos + n) of the DAP.  A pinned torch tensor is copied to the device straight
+        from where it is (it has to stay alive until finish()); anything else goes through the
+        stream's pinned staging."""
+        direct = isinstance(block, torch.Tensor) and block.is_pinned() and block.is_contiguous()
+        if isinstance(block, torch.Tensor) and not direct:
+            block = block.numpy()
+        if not direct:
+            block = np.asarray(block)
+        if block.ndim != 2 or block.shape[1] != self.C:
+            raise MemoError(f"DAP block must be [n, {self.C}]")
+        if block.shape[0] == 0:
+            return
+        done = 0
+        while done < block.shape[0]:
+            if self.fill == self.chunk_rows:
+                self._submit(last=False)
+            n = min(block.shape[0] - done, self.chunk_rows - self.fill)
+            if direct and self.fill == 0 and n == min(self.chunk_rows, block.shape[0] - done):
+                self.src = block[done:done + n]            # a whole chunk (or the block's tail) in place
+            else:
+                slot = self._fill_slot(self.k)
+                if slot["pin"] is None:
+                    slot["pin"] = torch.empty((self.chunk_rows, self.C), dtype=torch.int32, pin_memory=True)
+                if self.src is not None:                   # rows taken in place earlier join the staging
+                    m = self.src.shape[0]
+                    slot["pin"].numpy()[:m] = self.src.numpy()
+                    self.src = None
+                piece = block[done:done + n]
+                slot["pin"].numpy()[self.fill:self.fill + n] = piece.numpy() if direct else piece
+            self.fill += n
+            self.pos += n
+            done += n
+            tail = block[done - 1]
+            self.last_row = (tail.numpy() if direct else np.asarray(tail)).copy()
+
+    def finish(self) -> int:
+        """Flushes the last chunk and every pending result; returns the number of index rows."""
+        if self.fill:
+            self._submit(last=True)
+        while self.collected < self.k:
+            self._collect()
+        return self.n_out
+
+    # ---- one chunk
+    def _segments(self, pos0, n, halo, last):
+        segs = api.segments_for_rows(self.records, pos0, n, buffer_row0=1 if halo else 0,
+                                     primed_first=not halo, chr_end_last=True)
+        tail = segs[-1]
+        if not last and tail.pos0 + tail.n_rows < tail.rec_len:
+            tail.flags &= ~api.MEMO_SEG_CHR_END          # the record goes on in the next chunk
+        return segs
+
+    def _submit(self, last: bool) -> None:
+        while self.k - self.collected >= RING - 1:        # (one slot is being filled, RING - 1 in flight)
+            self._collect()
+        slot = self._fill_slot(self.k)
+        n = self.fill
+        pos0 = self.pos - n
+        if self.segs_all is not None:
+            # explicit runs over the rows fed: the previous row always travels with the chunk
+            a = pos0 - self.pos_stream0
+            halo = a > 0
+            segs = _clip_segments(self.segs_all, a, a + n, 1 if halo else 0)
+        else:
+            # the halo row = the record's previous row
+            halo = pos0 > self.pos_stream0 and pos0 not in self.starts
+            segs = self._segments(pos0, n, halo, last)
+        src = self.src if self.src is not None else slot["pin"][:n]
+        self.src = None
+        if halo:
+            slot["pin_halo"].numpy()[0] = self.prev_last_row
+        slot.update(n=n, pos0=pos0, halo=halo, last=last, segs=segs)
+        with torch.cuda.stream(self.copy_stream):
+            # (the build that read this slot's device buffer last is RING chunks back: collected)
+            # device chunk = [halo row,] rows: always starts at the (16-byte aligned) buffer base
+            if halo:
+                slot["dev"][0:1].copy_(slot["pin_halo"], non_blocking=True)
+            base = 1 if halo else 0
+            slot["dev"][base:base + n].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        slot["h2d"] = ev
+        self.main.wait_event(ev)
+        self.prev_last_row = self.last_row                 # next chunk's halo = this chunk's last row
+        if not self.general and segs:
+            self._launch_fast(slot)
+        slot["general"] = self.general
+        self.k += 1
+        self.fill = 0
+        if self.general:
+            while self.collected < self.k:                 # the exact build runs chunk by chunk
+                self._collect()
+
+    def _launch_fast(self, slot) -> None:
+        n_buf = slot["n"] + (1 if slot["halo"] else 0)
+        soe = torch.empty(max(len(slot["segs"]), 1), dtype=torch.int64, device=self.dev)
+        self.builder.launch(slot["dev"][:n_buf], self.C, slot["segs"], self.order,
+                            (slot["out"][0], slot["out"][1], slot["out"][2]), soe, result=slot["res"], **self.tuning)
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        with torch.cuda.stream(self.back_stream):
+            self.back_stream.wait_event(ev)
+            slot["pin_res"].copy_(slot["res"], non_blocking=True)
+            slot["pin_soe"] = soe.to("cpu", non_blocking=True)
+            if not self.on_device:
+                slot["pin_out"].copy_(slot["out"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.back_stream)
+        slot["soe"], slot["done"] = soe, done
+
+    def _collect(self) -> None:
+        slot = self._slot(self.collected)
+        self.collected += 1
+        if not slot["segs"]:
+            return                                         # rows that belong to no run
+        if not slot["general"]:
+            slot["done"].synchronize()
+            n_out, irregular = int(slot["pin_res"][RES_N_OUT]), bool(slot["pin_res"][RES_IRREGULAR])
+            if irregular:
+                # exact build from this chunk on; chunks already submitted behind it are redone too
+                self.general = True
+                pending = [self._slot(i) for i in range(self.collected, self.k)]
+                self._run_general(slot)
+                for other in pending:
+                    other["general"] = True
+                return
+            if n_out > self.cap:                          # denser than expected: once more with exact room
+                big = torch.empty((3, n_out), dtype=torch.int32, device=self.dev)
+                self.builder.launch(slot["dev"][:slot["n"] + (1 if slot["halo"] else 0)], self.C, slot["segs"], self.order,
+                                    (big[0], big[1], big[2]), slot["soe"], **self.tuning)
+                rows = big if self.on_device else big.cpu().numpy()
+                seg_ends = slot["soe"].cpu().tolist()
+            else:
+                rows = slot["out"][:, :n_out] if self.on_device else slot["pin_out"].numpy()[:, :n_out]
+                seg_ends = slot["pin_soe"].tolist()
+            self._deliver(slot, rows, seg_ends)
+        else:
+            self._run_general(slot)
+
+    def _run_general(self, slot) -> None:
+        C = self.C
+        buf = slot["dev"][:slot["n"] + (1 if slot["halo"] else 0)]
+        segs = slot["segs"]
+        soe = torch.empty(max(len(segs), 1), dtype=torch.int64, device=self.dev)
+        cin = None
+        if slot["halo"] and not (segs[0].flags & api.MEMO_SEG_PRIMED):
+            if self.carry is None:
+                # everything before this chunk was regular: the last flagged MEM of a column ends
+                # where the (sorted) MEM ends of the run's previous row do
+                e = buf[segs[0].row_begin - 1].to(torch.int64) + (segs[0].pos0 - 1)
+                self.carry = torch.sort(e, descending=True).values if self.order else e
+            cin = self.carry.to(torch.int32)              # wraps to the uint32 bit pattern
+        cout = torch.full((C,), -1, dtype=torch.int32, device=self.dev)
+        self.builder.launch(buf, C, segs, self.order, None, soe, general=True, carry_in=cin, carry_out=cout,
+                            **self.tuning)
+        n_out, _, _ = self.builder.result()
+        out = torch.empty((3, max(n_out, 1)), dtype=torch.int32, device=self.dev)
+        self.builder.launch(buf, C, segs, self.order, (out[0], out[1], out[2]), soe, general=True, carry_in=cin,
+                            carry_out=cout, **self.tuning)
+        self.builder.result()
+        co = cout.to(torch.int64) & 0xFFFFFFFF
+        keep = self.carry if (self.carry is not None and cin is not None) else torch.full_like(co, 0xFFFFFFFF)
+        self.carry = torch.where(co != 0xFFFFFFFF, co, keep)
+        self.n_chunks_general += 1
+        self._deliver(slot, out[:, :n_out] if self.on_device else out[:, :n_out].cpu().numpy(), soe.cpu().tolist())
+
+    def _deliver(self, slot, rows, seg_ends) -> None:
+        rec_counts, prev = [], 0
+        for s, e in zip(slot["segs"], seg_ends):
+            if e > prev:
+                if rec_counts and rec_counts[-1][0] == s.rec_id:
+                    rec_counts[-1] = (s.rec_id, rec_counts[-1][1] + e - prev)
+                else:
+                    rec_counts.append((s.rec_id, e - prev))
+            prev = e
+        self.n_out += prev
+        if prev and self.on_device:
+            self.on_rows(rec_counts, rows[:, :prev])
+        elif prev:
+            self.on_rows(rec_counts, rows[0, :prev], rows[1, :prev].view(np.uint32), rows[2, :prev])
+
+
+def build_index_streaming(blocks, records, order: bool, on_rows, n_cols: Optional[int] = None,
+                          pos_first: int = 0, device=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES,
+                          stats: Optional[dict] = None, **tuning) -> int:
+    """Index rows of a DAP that arrives as an iterator of int32 [n, C] blocks of consecutive rows
+    (first row = global position pos_first); on_rows as in IndexStream.  Returns the row count."""
+    stream = None
+    for block in blocks:
+        if stream is None:
+            C = block.shape[1] if n_cols is None else n_cols
+            stream = IndexStream(records, order, C, on_rows, device=device, chunk_bytes=chunk_bytes,
+                                 pos_first=pos_first, **tuning)
+        stream.feed(block)
+    if stream is None:
+        return 0
+    n = stream.finish()
+    if stats is not None:
+        stats.update(general=stream.general, n_out=n, chunks=stream.k, chunks_general=stream.n_chunks_general)
+    return n
+
+
 def build_index(dap_host, records: Optional[Sequence[Tuple[str, int]]], order: bool,
                 chunk_bytes: int = DEFAULT_CHUNK_BYTES, device=None, pos_first: int = 0,
                 stats: Optional[dict] = None, segs: Optional[List[api.Segment]] = None,
@@ -123,12 +402,12 @@ def build_index(dap_host, records: Optional[Sequence[Tuple[str, int]]], order: b
     """DAP on the host (int32 [L, C], row i = global position pos_first + i) ->
     index rows in the reference's print order (src/dap_to_bed.py --mem --overlap
     [--order]).  Returns (rec_idx, start, end, order) int64 numpy arrays, or an
-    IndexRowsHost (int32 columns, no widening) with raw=True.
+    IndexRowsHost (int32 columns in one pinned block, no widening) with raw=True.
 
     `segs` (explicit record runs over the rows of dap_host, e.g. a position shard
-    with halo rows) overrides the records/pos_first layout.  If the device reports
-    the input as irregular (not valid matching statistics) the exact three-pass
-    build is run on the whole DAP instead.
+    with halo rows) overrides the records/pos_first layout.  The DAP streams through
+    IndexStream: device memory and pinned staging are O(chunk_bytes), whatever L;
+    input that is not valid matching statistics switches to the exact build on the way.
     """
     host = _as_host_tensor(dap_host)
     if host.dtype != torch.int32 or host.dim() != 2:
@@ -139,111 +418,51 @@ def build_index(dap_host, records: Optional[Sequence[Tuple[str, int]]], order: b
         z = np.zeros(0, dtype=np.int64)
         res = IndexRowsHost([], z.astype(np.int32), z.astype(np.uint32), z.astype(np.int32), False)
         return res if raw else res.as_int64()
-    # explicit runs (position shards with halos) or the whole-file layout of index.sh:83
-    segs_all = list(segs) if segs is not None else \
+    if segs is None:
         api.segments_for_rows(records, pos_first, L)               # raises like the reference
-    if not host.is_pinned():
-        # pageable memory would serialise the copies with the kernels
-        staged = _pinned("dap", host.numel() * 4)[:host.numel() * 4].view(torch.int32).view(L, C)
-        staged.copy_(host)
-        host = staged
+    # index rows land in one pinned block, copied there chunk by chunk as they are built
+    state = {"blk": None, "arr": None, "n": 0, "cap": 0, "rec_counts": []}
 
-    builder = api.IndexBuilder(dev)
-    chunk_rows = max(1, min(L, chunk_bytes // (4 * C)))
-    bounds = list(range(0, L, chunk_rows)) + [L]
-    n_chunks = len(bounds) - 1
-    ring = [torch.empty((chunk_rows + 1, C), dtype=torch.int32, device=dev) for _ in range(min(RING, n_chunks))]
-    cap = max(1024, int(chunk_rows * C * 0.02) + 2 * C)
-    outs = torch.empty((n_chunks, 3, cap), dtype=torch.int32, device=dev)
-    results = torch.zeros((n_chunks, RES_SLOTS), dtype=torch.int64, device=dev)
-    main = torch.cuda.current_stream(dev)
-    copy_stream = torch.cuda.Stream(dev)
-    copy_stream.wait_stream(main)
-    done = [None] * n_chunks
-    chunk_segs, seg_ends = [], []
+    def room(n_more):
+        need = state["n"] + n_more
+        if need <= state["cap"]:
+            return
+        cap = max(need + need // 2, 1 << 16)
+        blk, raw_bytes = _pinned_result(12 * cap)
+        if state["n"]:
+            torch.cuda.current_stream(dev).synchronize()
+            raw_bytes.view(np.int32).reshape(3, cap)[:, :state["n"]] = state["arr"][:, :state["n"]]
+        state.update(blk=blk.view(torch.int32).view(3, cap), arr=raw_bytes.view(np.int32).reshape(3, cap), cap=cap)
 
-    def enqueue(i, cap_i, out_i):
-        a, b = bounds[i], bounds[i + 1]
-        lo = a - 1 if a > 0 else a                   # the halo row travels with the chunk
-        buf = ring[i % len(ring)]
-        if i >= len(ring):
-            copy_stream.wait_event(done[i - len(ring)])
-        with torch.cuda.stream(copy_stream):
-            buf[:b - lo].copy_(host[lo:b], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        main.wait_event(ev)
-        cs = _clip_segments(segs_all, a, b, a - lo)
-        soe = torch.empty(max(len(cs), 1), dtype=torch.int64, device=dev)
-        builder.launch(buf, C, cs, order, (out_i[0], out_i[1], out_i[2]), soe,
-                       result=results[i], **tuning)
-        done[i] = torch.cuda.Event()
-        done[i].record(main)
-        return cs, soe
+    def on_rows(rec_counts, dev_rows):
+        n = dev_rows.shape[1]
+        room(n)
+        state["blk"][:, state["n"]:state["n"] + n].copy_(dev_rows, non_blocking=True)
+        state["n"] += n
+        for rid, c in rec_counts:
+            if state["rec_counts"] and state["rec_counts"][-1][0] == rid:
+                state["rec_counts"][-1] = (rid, state["rec_counts"][-1][1] + c)
+            else:
+                state["rec_counts"].append((rid, c))
 
-    for i in range(n_chunks):
-        cs, soe = enqueue(i, cap, outs[i])
-        chunk_segs.append(cs)
-        seg_ends.append(soe)
-    res_host = results.cpu()                        # synchronises
-    if bool((res_host[:, RES_IRREGULAR] != 0).any()):
-        out = _build_index_general(host, C, segs_all, order, dev, builder, tuning)
-        if stats is not None:
-            stats.update(general=True, n_out=out.n)
-        return out if raw else out.as_int64()
-    counts = res_host[:, RES_N_OUT].tolist()
-    big = {}
-    for i, n in enumerate(counts):                  # denser than expected: redo with exact room
-        if n > cap:
-            big[i] = torch.empty((3, n), dtype=torch.int32, device=dev)
-            copy_stream.wait_stream(main)          # the ring slot may still be in use by a retry
-            chunk_segs[i], seg_ends[i] = enqueue(i, n, big[i])
-    total = int(sum(counts))
-    arr = None
-    if total:
-        blk, raw_bytes = _pinned_result(12 * total)
-        stage = blk.view(torch.int32).view(3, total)
-        arr = raw_bytes.view(np.int32).reshape(3, total)
-        off = 0
-        for i, n in enumerate(counts):
-            if n:
-                src = big[i] if i in big else outs[i]
-                stage[:, off:off + n].copy_(src[:, :n], non_blocking=True)
-                off += n
-    width = max(len(cs) for cs in chunk_segs)
-    seg_end_host = torch.stack([torch.nn.functional.pad(s, (0, width - s.numel())) for s in seg_ends]).cpu() \
-        if width else None                           # one copy; synchronises the row copies too
+    chunk_rows = max(1, chunk_bytes // (4 * C))
+    room(int(L * C * 0.022) + 4 * C)
+    stream = IndexStream(records, order, C, on_rows, device=dev, chunk_bytes=chunk_bytes, pos_first=pos_first,
+                         segs_all=list(segs) if segs is not None else None, on_device=True, **tuning)
+    for a in range(0, L, chunk_rows):
+        stream.feed(host[a:a + chunk_rows])
+    total = stream.finish()
     torch.cuda.current_stream(dev).synchronize()
-    rec_counts = []
-    for ci, cs in enumerate(chunk_segs):
-        prev = 0
-        for s, e in zip(cs, seg_end_host[ci].tolist()):
-            if e > prev:
-                if rec_counts and rec_counts[-1][0] == s.rec_id:
-                    rec_counts[-1] = (s.rec_id, rec_counts[-1][1] + e - prev)
-                else:
-                    rec_counts.append((s.rec_id, e - prev))
-            prev = e
     if total:
-        out = IndexRowsHost(rec_counts, arr[0], arr[1].view(np.uint32), arr[2], False)
+        arr = state["arr"]
+        out = IndexRowsHost(state["rec_counts"], arr[0, :total], arr[1, :total].view(np.uint32), arr[2, :total],
+                            stream.general)
     else:
         z = np.zeros(0, dtype=np.int32)
-        out = IndexRowsHost([], z, z.view(np.uint32), z.copy(), False)
+        out = IndexRowsHost([], z, z.view(np.uint32), z.copy(), stream.general)
     if stats is not None:
-        stats.update(general=False, n_out=total, chunks=n_chunks)
+        stats.update(general=stream.general, n_out=total, chunks=stream.k)
     return out if raw else out.as_int64()
-
-
-def _build_index_general(host, C, segs_all, order, dev, builder, tuning) -> IndexRowsHost:
-    """Irregular input: the whole DAP goes to the device and the exact build runs."""
-    dap = torch.empty(tuple(host.shape), dtype=torch.int32, device=dev)
-    dap.copy_(host, non_blocking=True)
-    res = builder.build(dap, C, segs_all, order, force_general=True, **tuning)
-    n = res.n
-    counts = np.diff(np.concatenate([[0], res.seg_out_end.numpy()]))
-    rec_counts = [(rid, int(c)) for rid, c in zip(res.seg_rec_id, counts) if c]
-    return IndexRowsHost(rec_counts, res.start[:n].cpu().numpy(),
-                         res.end[:n].cpu().numpy().view(np.uint32), res.order[:n].cpu().numpy(), True)
 
 
 def _rows_to_device(f1, f2, f3, dev, trusted=False):

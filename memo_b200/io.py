@@ -54,6 +54,113 @@ def read_dap_text(path) -> Tuple[int, np.ndarray]:
     return int(pos[0]), out
 
 
+def iter_dap_text(path, block_bytes: int = 64 << 20):
+    """dap.txt streamed in blocks (the reference streams it row by row, src/dap_to_bed.py:14-18):
+    yields (first position, int32 [n, C]) for consecutive runs of rows; memory use is
+    O(block_bytes).  Same validation as read_dap_text."""
+    with open(path, "rb") as fh:
+        first = fh.readline()
+    n_fields = len(first.split(b" ")) if first.strip() else 0
+    if n_fields == 0:
+        return
+    if n_fields < 2:
+        raise MemoError("dap.txt needs a position column and at least one genome column")
+    names = [f"f{i}" for i in range(n_fields)]
+    try:
+        reader = pacsv.open_csv(
+            path,
+            read_options=pacsv.ReadOptions(column_names=names, block_size=block_bytes),
+            parse_options=pacsv.ParseOptions(delimiter=" "),
+            convert_options=pacsv.ConvertOptions(column_types={n: pa.int64() for n in names}),
+        )
+        expect = None
+        for batch in reader:
+            n = batch.num_rows
+            if n == 0:
+                continue
+            cols = batch.columns
+            for i, col in enumerate(cols):
+                if col.null_count:
+                    raise ValueError(f"invalid literal for int() in DAP column {i}")
+            pos = cols[0].to_numpy(zero_copy_only=False)
+            if (n > 1 and not (np.diff(pos) == 1).all()) or (expect is not None and int(pos[0]) != expect):
+                raise MemoError("dap.txt positions are not consecutive (expected `nl -v0` numbering)")
+            expect = int(pos[-1]) + 1
+            out = np.empty((n, n_fields - 1), dtype=np.int32)
+            for j in range(1, n_fields):
+                a = cols[j].to_numpy(zero_copy_only=False)
+                if a.min() < 0 or a.max() > 2**31 - 1:
+                    raise MemoError("DAP lengths must be in [0, 2^31)")
+                out[:, j - 1] = a
+            yield int(pos[0]), out
+    except pa.ArrowInvalid as e:                  # int() in the reference (src/dap_to_bed.py:87)
+        raise ValueError(f"invalid literal for int() in dap.txt: {e}") from None
+
+
+def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 20, read_bytes: int = 4 << 20):
+    """Per-genome MONI `*.lengths` / `*.lengths.vert` files streamed side by side: yields int32
+    [n, C] blocks of consecutive pivot positions (all files advance together; memory use is
+    O(C * block)).  Same semantics as read_lengths_columns."""
+    if not paths:
+        raise MemoError("at least one .lengths file is needed")
+
+    class _Col:
+        def __init__(self, path):
+            self.path, self.fh, self.tail, self.vals, self.done = path, open(path, "rb"), b"", [], False
+            self.have = 0
+
+        def fill(self, want):
+            while self.have < want and not self.done:
+                data = self.fh.read(read_bytes)
+                if not data:
+                    self.done = True
+                    data, self.tail = self.tail + b"\n", b""
+                else:
+                    data = self.tail + data
+                    cut = max(data.rfind(b"\n"), data.rfind(b" "))
+                    data, self.tail = data[:cut + 1], data[cut + 1:]
+                if b">" in data:
+                    data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b">"))
+                if _NOT_LENGTHS.search(data):
+                    raise ValueError(f"invalid literal for int() in {self.path}")
+                if not data.strip():
+                    continue
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", DeprecationWarning)
+                    v = np.fromstring(data.decode("ascii"), dtype=np.int64, sep=" ")
+                if v.size:
+                    if v.min() < 0 or v.max() > 2**31 - 1:
+                        raise MemoError("DAP lengths must be in [0, 2^31)")
+                    self.vals.append(v.astype(np.int32))
+                    self.have += v.size
+
+        def take(self, n):
+            buf = np.concatenate(self.vals) if len(self.vals) != 1 else self.vals[0]
+            out, rest = buf[:n], buf[n:]
+            self.vals, self.have = ([rest] if rest.size else []), rest.size
+            return out
+
+    cols = [_Col(p) for p in paths]
+    try:
+        while True:
+            for c in cols:
+                c.fill(block_rows)
+            n = min(c.have for c in cols)
+            if n == 0:
+                for c in cols:
+                    if c.have:
+                        raise MemoError(f"{c.path}: more lengths than {cols[0].path} (one per pivot position)")
+                return
+            n = min(n, block_rows)
+            out = np.empty((n, len(cols)), dtype=np.int32)
+            for j, c in enumerate(cols):
+                out[:, j] = c.take(n)
+            yield out
+    finally:
+        for c in cols:
+            c.fh.close()
+
+
 def read_lengths_columns(paths: Sequence[str], threads: int = 8) -> np.ndarray:
     """Per-genome MONI `*.lengths` (or the `*.lengths.vert` index.sh:79 makes of them) ->
     int32 [L, C] DAP matrix, one column per file in the order given (genome_list.txt
@@ -99,6 +206,15 @@ def index_table(records: Sequence[Tuple[str, int]], rec_idx, start, end, order) 
     return pa.table([f0, pa.array(np.asarray(start, dtype=np.int64)),
                      pa.array(np.asarray(end, dtype=np.int64)),
                      pa.array(np.asarray(order, dtype=np.int64))], schema=INDEX_SCHEMA)
+
+
+def index_batch(names: pa.Array, rec_counts, start, end, order) -> pa.Table:
+    """Arrow table of one batch of index rows: rec_counts = [(record index, rows)] in row order,
+    start / end / order int32 / uint32 / int32 numpy columns."""
+    ids = np.repeat(np.array([r for r, _ in rec_counts], dtype=np.int64),
+                    np.array([c for _, c in rec_counts], dtype=np.int64))
+    return pa.table([pc.take(names, pa.array(ids)), pa.array(start.astype(np.int64)),
+                     pa.array(end.astype(np.int64)), pa.array(order.astype(np.int64))], schema=INDEX_SCHEMA)
 
 
 def write_bed(table: pa.Table, sink=None) -> None:

@@ -389,6 +389,83 @@ def test_host_build_index_irregular_falls_back():
     assert_index_equal(got, mo.index_build(vals, recs, True), "irregular")
 
 
+def _stream_rows(blocks, recs, order, **kw):
+    from memo_b200 import host
+    parts, stats = [], {}
+
+    def on_rows(rec_counts, start, end, col):
+        rec = np.repeat([r for r, _ in rec_counts], [c for _, c in rec_counts]).astype(np.int64)
+        parts.append((rec, start.astype(np.int64), end.astype(np.int64), col.astype(np.int64)))
+
+    n = host.build_index_streaming(blocks, recs, order, on_rows, stats=stats, **kw)
+    got = tuple(np.concatenate([p[i] for p in parts]) if parts else np.zeros(0, dtype=np.int64) for i in range(4))
+    assert n == got[1].size
+    return got, stats
+
+
+@pytest.mark.parametrize("order", [True, False])
+def test_index_stream_blocks_of_any_size(order):
+    """The streaming pipeline behind the dap_to_bed drop-in: blocks of arbitrary sizes in, index
+    rows out chunk by chunk; chunk cuts inside records, at record ends, one-row records, a DAP
+    that stops inside its last record, pinned blocks taken in place."""
+    C = 7
+    lens = [3000, 1, 4500, 1, 1, 2500]
+    recs = [(f"c{i}", n) for i, n in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=50 + i, dense=(i % 2 == 0)) for i, n in enumerate(lens)])
+    vals = np.ascontiguousarray(vals[:-37], dtype=np.int32)
+    want = mo.index_build(vals, recs, order)
+    rng = np.random.default_rng(4)
+    for chunk_rows in (1, 333, 3000, 3001, 5000, 10 ** 6):
+        cuts = np.sort(rng.integers(0, len(vals), 9))
+        blocks = [b for b in np.split(vals, cuts)]
+        got, stats = _stream_rows(iter(blocks), recs, order, chunk_bytes=4 * C * chunk_rows)
+        assert_index_equal(got, want, f"chunk_rows={chunk_rows}")
+        assert not stats["general"]
+    pinned = torch.from_numpy(vals).pin_memory()
+    got, _ = _stream_rows(iter([pinned[:4000], pinned[4000:4001], pinned[4001:]]), recs, order, chunk_bytes=4 * C * 1500)
+    assert_index_equal(got, want, "pinned blocks")
+    # a stream that starts inside a record (dap.txt whose first position is not 0)
+    got, _ = _stream_rows(iter([vals[700:]]), recs, order, chunk_bytes=4 * C * 1000, pos_first=700)
+    assert_index_equal(got, mo.index_build(vals[700:], recs, order, pos=np.arange(700, len(vals))), "pos_first")
+
+
+@pytest.mark.parametrize("order", [True, False])
+def test_index_stream_turns_exact_where_input_turns_irregular(order):
+    """Valid matching statistics, then arbitrary integers from the middle of a record on: the
+    chunks before stay single-pass, the rest runs the exact build with the carry handed on."""
+    C = 5
+    rng = np.random.default_rng(8)
+    valid = mo.synth_dap(9000, C, seed=3, dense=True)
+    junk = rng.integers(0, 60, (6000, C))
+    junk[rng.random(junk.shape) < 0.4] = 0
+    junk[:, 0] = np.maximum(7000 - 2 * np.arange(6000), 0)          # carries that cross many chunks
+    vals = np.ascontiguousarray(np.concatenate([valid[:5000], junk, valid[5000:]]), dtype=np.int32)
+    recs = [("a", 8000), ("b", 4000), ("c", 3000)]
+    want = mo.index_build(vals, recs, order)
+    for chunk_rows in (700, 2048, 10 ** 6):
+        got, stats = _stream_rows(iter([vals]), recs, order, chunk_bytes=4 * C * chunk_rows)
+        assert_index_equal(got, want, f"chunk_rows={chunk_rows}")
+        assert stats["general"] and (chunk_rows > 5000 or stats["chunks_general"] < stats["chunks"])
+
+
+def test_index_stream_memory_is_bounded_by_the_chunk():
+    """3 M rows through 1 MB chunks: device memory stays O(chunk), not O(DAP)."""
+    from memo_b200 import api
+    L, C = 3_000_000, 9
+    dap = api.synth_dap(L, C, seed=11).cpu().numpy()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    got, stats = _stream_rows((dap[a:a + 250_000] for a in range(0, L, 250_000)), [("chrS", L)], True,
+                              chunk_bytes=1 << 20)
+    peak = torch.cuda.max_memory_allocated() - base
+    assert stats["chunks"] >= 100 and peak < 32 << 20, (stats, peak)
+    want_head = mo.index_build(dap[:200_000], [("chrS", 200_000)], True)
+    m = got[1] < 199_000
+    assert np.array_equal(got[1][m], want_head[1][want_head[1] < 199_000])
+
+
 def test_host_query_matches_oracle():
     from memo_b200 import host
     C, L = 9, 40000
