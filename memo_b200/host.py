@@ -135,11 +135,14 @@ class IndexStream:
 
     def __init__(self, records: Optional[Sequence[Tuple[str, int]]], order: bool, n_cols: int, on_rows,
                  device=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES, pos_first: int = 0,
-                 segs_all: Optional[List[api.Segment]] = None, on_device: bool = False, **tuning):
+                 segs_all: Optional[List[api.Segment]] = None, on_device: bool = False,
+                 first_halo=None, **tuning):
         """segs_all: explicit record runs over the rows fed (row 0 = the first row fed), e.g. a
         position shard with halo rows, instead of the records / pos_first layout of index.sh:83.
         on_device: on_rows receives a DEVICE tensor int32 [3, n] (valid until the stream's main
-        CUDA stream has run RING - 1 more chunks) instead of host views."""
+        CUDA stream has run RING - 1 more chunks) instead of host views.
+        first_halo: the DAP row before the first row fed (int [C]) when the stream is a position
+        shard that starts inside a record: the first run then continues that record."""
         self.records, self.order, self.C, self.on_rows, self.tuning = list(records or []), order, n_cols, on_rows, tuning
         self.segs_all, self.on_device = segs_all, on_device
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -162,7 +165,9 @@ class IndexStream:
             acc += length
         self.src = None                     # rows of the current chunk taken in place (pinned caller memory)
         self.last_row = None                # last row fed so far
-        self.prev_last_row = None           # last row of the chunk submitted before the current one
+        # last row of the chunk submitted before the current one
+        self.prev_last_row = None if first_halo is None else np.asarray(first_halo, dtype=np.int32).copy()
+        self.first_halo = first_halo is not None
         self.general = False                # exact build from here on (irregular input seen)
         self.carry = None                   # device int64 [C]: per-column end of the last flagged MEM
         self.n_out = 0
@@ -228,10 +233,12 @@ class IndexStream:
             tail = block[done - 1]
             self.last_row = (tail.numpy() if direct else np.asarray(tail)).copy()
 
-    def finish(self) -> int:
-        """Flushes the last chunk and every pending result; returns the number of index rows."""
+    def finish(self, final: bool = True) -> int:
+        """Flushes the last chunk and every pending result; returns the number of index rows.
+        final=False: the DAP goes on in another position shard (no chr-end rows after a last run
+        that stops inside its record)."""
         if self.fill:
-            self._submit(last=True)
+            self._submit(last=final)
         while self.collected < self.k:
             self._collect()
         return self.n_out
@@ -258,7 +265,7 @@ class IndexStream:
             segs = _clip_segments(self.segs_all, a, a + n, 1 if halo else 0)
         else:
             # the halo row = the record's previous row
-            halo = pos0 > self.pos_stream0 and pos0 not in self.starts
+            halo = (pos0 > self.pos_stream0 or self.first_halo) and pos0 not in self.starts
             segs = self._segments(pos0, n, halo, last)
         src = self.src if self.src is not None else slot["pin"][:n]
         self.src = None
@@ -377,19 +384,20 @@ class IndexStream:
 
 def build_index_streaming(blocks, records, order: bool, on_rows, n_cols: Optional[int] = None,
                           pos_first: int = 0, device=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES,
-                          stats: Optional[dict] = None, **tuning) -> int:
+                          stats: Optional[dict] = None, first_halo=None, final: bool = True, **tuning) -> int:
     """Index rows of a DAP that arrives as an iterator of int32 [n, C] blocks of consecutive rows
-    (first row = global position pos_first); on_rows as in IndexStream.  Returns the row count."""
+    (first row = global position pos_first); on_rows as in IndexStream.  first_halo / final: the
+    stream is one position shard of a larger DAP (IndexStream).  Returns the row count."""
     stream = None
     for block in blocks:
         if stream is None:
             C = block.shape[1] if n_cols is None else n_cols
             stream = IndexStream(records, order, C, on_rows, device=device, chunk_bytes=chunk_bytes,
-                                 pos_first=pos_first, **tuning)
+                                 pos_first=pos_first, first_halo=first_halo, **tuning)
         stream.feed(block)
     if stream is None:
         return 0
-    n = stream.finish()
+    n = stream.finish(final)
     if stats is not None:
         stats.update(general=stream.general, n_out=n, chunks=stream.k, chunks_general=stream.n_chunks_general)
     return n

@@ -2,6 +2,8 @@
 writers and readers.  Format conversion only -- no index arithmetic here."""
 from __future__ import annotations
 
+import io as _pyio
+import os as _os
 import re
 import sys
 import warnings
@@ -54,11 +56,71 @@ def read_dap_text(path) -> Tuple[int, np.ndarray]:
     return int(pos[0]), out
 
 
-def iter_dap_text(path, block_bytes: int = 64 << 20):
+class _RangeFile(_pyio.RawIOBase):
+    """Bytes [lo, hi) of a file as a read-only stream (a rank's share of dap.txt)."""
+
+    def __init__(self, path, lo, hi):
+        super().__init__()
+        self.fh, self.left = open(path, "rb"), hi - lo
+        self.fh.seek(lo)
+
+    def readable(self):
+        return True
+
+    def readinto(self, b):
+        n = min(len(b), self.left)
+        if n <= 0:
+            return 0
+        got = self.fh.readinto(memoryview(b)[:n])
+        self.left -= got
+        return got
+
+    def close(self):
+        self.fh.close()
+        super().close()
+
+
+def split_text_rows(path, world: int, rank: int):
+    """A rank's share of a text file of rows, cut at line starts near equal byte offsets:
+    (byte_lo, byte_hi, the line before byte_lo or None).  Shares of all ranks tile the file."""
+    size = _os.path.getsize(path)
+
+    def line_start(target):
+        if target <= 0:
+            return 0
+        if target >= size:
+            return size
+        with open(path, "rb") as fh:
+            fh.seek(target - 1)
+            while True:                                    # first line start at or after target
+                chunk = fh.read(1 << 16)
+                if not chunk:
+                    return size
+                i = chunk.find(b"\n")
+                if i >= 0:
+                    return fh.tell() - len(chunk) + i + 1
+
+    lo, hi = line_start(size * rank // world), line_start(size * (rank + 1) // world)
+    prev = None
+    if lo > 0:
+        with open(path, "rb") as fh:
+            back = min(lo, 1 << 20)
+            fh.seek(lo - back)
+            tail = fh.read(back)
+            prev = tail[:-1].rsplit(b"\n", 1)[-1]
+    return lo, hi, prev
+
+
+def iter_dap_text(path, block_bytes: int = 64 << 20, byte_range=None):
     """dap.txt streamed in blocks (the reference streams it row by row, src/dap_to_bed.py:14-18):
     yields (first position, int32 [n, C]) for consecutive runs of rows; memory use is
-    O(block_bytes).  Same validation as read_dap_text."""
+    O(block_bytes).  Same validation as read_dap_text.  byte_range = (lo, hi): only the lines in
+    those bytes (a rank's share, split_text_rows)."""
+    lo, hi = byte_range if byte_range is not None else (0, _os.path.getsize(path))
+    if hi <= lo:
+        return
     with open(path, "rb") as fh:
+        fh.seek(lo)
         first = fh.readline()
     n_fields = len(first.split(b" ")) if first.strip() else 0
     if n_fields == 0:
@@ -68,7 +130,7 @@ def iter_dap_text(path, block_bytes: int = 64 << 20):
     names = [f"f{i}" for i in range(n_fields)]
     try:
         reader = pacsv.open_csv(
-            path,
+            pa.PythonFile(_RangeFile(path, lo, hi), mode="r"),
             read_options=pacsv.ReadOptions(column_names=names, block_size=block_bytes),
             parse_options=pacsv.ParseOptions(delimiter=" "),
             convert_options=pacsv.ConvertOptions(column_types={n: pa.int64() for n in names}),

@@ -102,6 +102,32 @@ def ordered_offsets(n_local: torch.Tensor, group=None) -> Tuple[torch.Tensor, to
     return counts, counts[:rank].sum()
 
 
+def ordered_file_write(part_path: str, out_path: str, device, group=None) -> int:
+    """The final ordered write of a sharded build: every rank holds its share of the output
+    (BED text, in the reference's print order) in `part_path`; the byte counts are all-gathered,
+    their exclusive prefix is a rank's offset in `out_path`, every rank copies its part there and
+    removes it.  Returns the total size."""
+    import os
+    import shutil
+    size = torch.tensor([os.path.getsize(part_path)], dtype=torch.int64, device=device)
+    counts, offset = ordered_offsets(size, group)
+    total = int(counts.sum().item())
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else 0
+    if rank == 0:
+        with open(out_path, "wb") as fh:
+            fh.truncate(total)
+    if multi:
+        dist.barrier(group=group)
+    with open(part_path, "rb") as src, open(out_path, "r+b") as dst:
+        dst.seek(int(offset.item()))
+        shutil.copyfileobj(src, dst, 16 << 20)
+    if multi:
+        dist.barrier(group=group)
+    os.remove(part_path)
+    return total
+
+
 def _world(group=None) -> int:
     return dist.get_world_size(group) if dist.is_initialized() else 1
 

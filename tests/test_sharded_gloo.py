@@ -131,3 +131,65 @@ def test_build_index_sharded_refuses_cpu():
     plan = shard.plan_shard([("a", 10)], 10, 1, 0)
     with pytest.raises(_lib.MemoError):
         shard.build_index_sharded(torch.zeros((10, 3), dtype=torch.int32), plan, 3, True)
+
+
+def _text_worker(rank, world, port, dap_path, out_path, lens, order, q):
+    """A rank of the sharded dap_to_bed, with the C oracle standing in for the device build:
+    byte share of dap.txt + the line before it -> BED part -> ordered_file_write."""
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from memo_b200 import io, shard
+        from oracle import c_oracle as co
+        from oracle import memo_oracle as mo
+        recs = [(f"c{i}", l) for i, l in enumerate(lens)]
+        lo, hi, prev = io.split_text_rows(dap_path, world, rank)
+        blocks = list(io.iter_dap_text(dap_path, block_bytes=1 << 14, byte_range=(lo, hi)))
+        part = f"{out_path}.part{rank:03d}"
+        with open(part, "w") as fh:
+            if blocks:
+                pos0 = blocks[0][0]
+                vals = np.concatenate([b for _, b in blocks])
+                starts = set(np.cumsum([0] + lens[:-1]).tolist())
+                halo = prev is not None and pos0 not in starts
+                buf = np.vstack([[int(x) for x in prev.split()][1:], vals]) if halo else vals
+                segs = co.make_segs(recs, len(vals), pos_first=pos0, row0=1 if halo else 0,
+                                    primed_first=not halo, chr_end_last=True)
+                tail = segs[-1]
+                if rank != world - 1 and tail.pos0 + tail.n_rows < tail.rec_len:
+                    tail.flags &= ~2
+                fh.write(mo.format_bed(recs, *co.index_build(buf, recs, order, segs=segs)))
+        shard.ordered_file_write(part, out_path, torch.device("cpu"))
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:                                         # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_text_shares_and_ordered_write_gloo(world, tmp_path):
+    from oracle import c_oracle as co
+    from oracle import memo_oracle as mo
+    lens = [4000, 1, 2500, 3300]
+    recs = [(f"c{i}", l) for i, l in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, 4, seed=31 + i, dense=True) for i, n in enumerate(lens)])[:-55]
+    dap = tmp_path / "dap.txt"
+    dap.write_text("".join(f"{i} " + " ".join(map(str, row)) + "\n" for i, row in enumerate(vals)))
+    out = tmp_path / "out.bed"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_text_worker, args=(r, world, port, str(dap), str(out), lens, True, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
+    assert out.read_text() == mo.format_bed(recs, *co.index_build(vals, recs, True))
+    assert not list(tmp_path.glob("out.bed.part*"))
