@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 4
+#define MEMO_B200_ABI_VERSION 5
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -194,6 +194,16 @@ int memo_format_conservation(const void* vals, int32_t is_u16, int64_t n, char* 
                              void* stream);
 int memo_format_membership(const uint32_t* bits, int64_t W, int32_t n_docs, char* out_text,
                            void* stream);
+
+/* `memo view` binning.  Replaces src/plot_conservation.py preprocess_data :46-58: per
+ * position bin, the number of positions holding each conservation value 0 .. n_docs.
+ *  vals    device uint8 [n] (uint16 with is_u16): a conservation vector (memo_query_conservation)
+ *  edges   device int64 [n_bins + 1]: bin b = positions [edges[b], edges[b+1]); the host
+ *          computes them as the reference does, int(linspace(0, n, n_bins + 1)) (:52)
+ *  counts  device uint64 [n_bins, n_docs + 1], zeroed here
+ *  status  device int32 [1]: set to 1 if a value above n_docs was seen (not counted) */
+int memo_view_bins(const void* vals, int32_t is_u16, int64_t n, int32_t n_docs, int32_t n_bins,
+                   const int64_t* edges, uint64_t* counts, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

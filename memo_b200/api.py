@@ -328,6 +328,33 @@ def format_membership(bits: torch.Tensor, n_docs: int) -> bytes:
 
 
 # --------------------------------------------------------------------------
+# view binning
+# --------------------------------------------------------------------------
+def view_bin_edges(n_positions: int, n_bins: int) -> np.ndarray:
+    """Bin edges exactly as src/plot_conservation.py:52: int(linspace(0, positions, n_bins + 1))."""
+    return np.array(list(map(int, np.linspace(0, n_positions, n_bins + 1))), dtype=np.int64)
+
+
+def view_bins(vals: torch.Tensor, n_docs: int, n_bins: int) -> np.ndarray:
+    """Per-bin counts of the conservation values 0 .. n_docs (uint64 numpy [n_bins, n_docs + 1])
+    of a device conservation vector (src/plot_conservation.py:46-58, the Counter per bin)."""
+    lib = _lib.load()
+    _require_cuda(vals, "vals")
+    if vals.dtype not in (torch.uint8, torch.int16):
+        raise MemoError("vals must be a uint8 / int16-typed uint16 conservation vector")
+    dev = vals.device
+    n = vals.numel()
+    edges = torch.from_numpy(view_bin_edges(n, n_bins)).to(dev)
+    counts = torch.empty((n_bins, n_docs + 1), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.memo_view_bins(_ptr(vals), 1 if vals.dtype == torch.int16 else 0, n, n_docs, n_bins,
+                            edges.data_ptr(), counts.data_ptr(), status.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "memo_view_bins")
+    # (values above n_docs are not in the table but stay in the bin sizes, as in the reference)
+    return counts.cpu().numpy().view(np.uint64)
+
+
+# --------------------------------------------------------------------------
 # synthetic DAP
 # --------------------------------------------------------------------------
 def synth_dap(rec_len: int, n_cols: int, seed: int, row0: int = 0, rows: Optional[int] = None,

@@ -14,7 +14,10 @@ Extensions (not in the reference):
       dap.txt), one process per GPU (torch.distributed.run, NCCL); every rank builds the rows
       of its shard from its own lines plus the line before them, the byte counts of the BED
       parts are all-gathered and every rank writes its part at its offset: the same bytes as
-      one GPU writes.  Without --out the result still goes to stdout.
+      one GPU writes.  Without --out the result still goes to stdout;
+  --parquet P.parquet   the index rows go from the device columns straight into the Parquet
+      index (schema, codec and row order of parquet_compress_bed.py; row groups cut at record
+      changes with min/max statistics), no BED text in between.
 """
 import argparse
 import os
@@ -40,6 +43,8 @@ def parse_arguments(argv=None):
                     help="extension: position-shard the DAP over N GPUs of this box (needs --dap)")
     ap.add_argument("--out", dest="out_path", default=None,
                     help="extension: write the BED to this file instead of stdout")
+    ap.add_argument("--parquet", dest="parquet_path", default=None,
+                    help="extension: write the Parquet index directly (no BED text, no parquet_compress_bed)")
     return ap.parse_args(argv)
 
 
@@ -63,6 +68,8 @@ def check_args(args):
         raise Exception("Error: Can only print overlaps if printing MEMs.")
     if args.gpus > 1 and args.dap_path is None:
         raise Exception("Error: --gpus needs --dap (position shards are byte shares of dap.txt).")
+    if args.parquet_path is not None and (args.gpus > 1 or args.out_path is not None):
+        raise Exception("Error: --parquet is a single-process output of its own (no --gpus, no --out).")
 
 
 def dap_blocks(args):
@@ -89,8 +96,12 @@ def _stream(args, records, sink, pos0, blocks, **kw):
     from . import host, io
     names = pa.array([r[0] for r in records], type=pa.utf8())
 
-    def on_rows(rec_counts, start, end, order):          # BED rows of one chunk, in print order
-        io.write_bed(io.index_batch(names, rec_counts, start, end, order), sink)
+    def on_rows(rec_counts, start, end, order):          # rows of one chunk, in print order
+        table = io.index_batch(names, rec_counts, start, end, order)
+        if isinstance(sink, io.IndexParquetWriter):
+            sink.write(table)
+        else:
+            io.write_bed(table, sink)
 
     chunk_bytes = int(os.environ.get("MEMO_CHUNK_BYTES", host.DEFAULT_CHUNK_BYTES))
     stats = {}
@@ -112,7 +123,13 @@ def main(args, sink=None):
         return main_rank(args, records)                   # one of the N processes of --gpus N
     if args.gpus > 1:
         return main_spawn(args, sink)
-    out = open(args.out_path, "wb") if args.out_path and sink is None else None
+    from . import io
+    out = None
+    if args.parquet_path is not None:
+        # index rows straight from the device columns into Parquet (skips the BED text and its re-parse)
+        out = io.IndexParquetWriter(args.parquet_path)
+    elif args.out_path and sink is None:
+        out = open(args.out_path, "wb")
     try:
         pos0, blocks = dap_blocks(args)
         stats = _stream(args, records, out or sink or sys.stdout.buffer, pos0, blocks)

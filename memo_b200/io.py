@@ -288,14 +288,99 @@ def write_bed(table: pa.Table, sink=None) -> None:
         include_header=False, delimiter="\t", quoting_style="none"))
 
 
+class IndexParquetWriter:
+    """Parquet index (schema f0:string, f1..f3:int64, ZSTD -- src/parquet_compress_bed.py:19-38)
+    written incrementally with row groups sized for the query's predicates: a row group holds
+    about `rows_per_group` rows and, where a record is large enough, rows of one record only,
+    so that the f0 / f1 min-max statistics of a group bound a position range of one record and
+    read_index_rows can skip every group a window does not touch (src/memo_query.py:25-27 scans
+    the whole file).  Row order, schema and codec are the reference's; row-group boundaries are
+    not observable by memo_query.py."""
+
+    def __init__(self, path, codec: str = "ZSTD", rows_per_group: int = 1 << 21):
+        self.rows_per_group = int(rows_per_group)
+        self.writer = pq.ParquetWriter(path, INDEX_SCHEMA, compression=codec, write_statistics=True)
+        self.pending = []                 # tables of the group being collected
+        self.n_pending = 0
+        self.last_f0 = None
+        self.n_rows = 0
+
+    def write(self, table: pa.Table) -> None:
+        """Rows in index order (any batch size)."""
+        if table.num_rows == 0:
+            return
+        table = table.cast(INDEX_SCHEMA)
+        f0 = table.column("f0").combine_chunks()
+        # cut the batch where the record changes
+        change = pc.not_equal(f0.slice(1), f0.slice(0, len(f0) - 1)).to_numpy(zero_copy_only=False)
+        cuts = [0] + (np.flatnonzero(change) + 1).tolist() + [table.num_rows]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            name = f0[a].as_py()
+            # a new record starts a new group once the current one is worth a group of its own
+            if self.last_f0 is not None and name != self.last_f0 and self.n_pending >= self.rows_per_group // 8:
+                self._flush()
+            self.last_f0 = name
+            pos = a
+            while pos < b:
+                take = min(b - pos, self.rows_per_group - self.n_pending)
+                self.pending.append(table.slice(pos, take))
+                self.n_pending += take
+                pos += take
+                if self.n_pending >= self.rows_per_group:
+                    self._flush()
+
+    def _flush(self) -> None:
+        if self.n_pending:
+            t = pa.concat_tables(self.pending).combine_chunks()
+            self.writer.write_table(t, row_group_size=t.num_rows)
+            self.n_rows += t.num_rows
+        self.pending, self.n_pending = [], 0
+
+    def close(self) -> None:
+        self._flush()
+        self.writer.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def write_parquet(table: pa.Table, path, codec: str = "ZSTD") -> None:
     pq.write_table(table, path, compression=codec)
 
 
-def read_index_rows(path, record: str, f1_gt: int, f1_lt: int):
+def read_index_rows(path, record: str, f1_gt: int, f1_lt: int, stats: dict = None):
     """Index rows of `record` with f1_gt < f1 < f1_lt (the live predicate of
-    memo_query.py:25-27; the other predicate's rows can never paint)."""
-    dataset = pads.dataset(path, format="parquet")
-    flt = (pads.field("f0") == record) & (pads.field("f1") > f1_gt) & (pads.field("f1") < f1_lt)
-    t = dataset.to_table(filter=flt, columns=["f1", "f2", "f3"])
+    memo_query.py:25-27; the other predicate's rows can never paint).  Only the row
+    groups whose f0 / f1 statistics admit such a row are read (IndexParquetWriter sizes the
+    groups for that; a file without statistics is read whole); `stats` receives the counts."""
+    pf = pq.ParquetFile(path)
+    md = pf.metadata
+    names = md.schema.names
+    c0, c1 = names.index("f0"), names.index("f1")
+    keep = []
+    for g in range(md.num_row_groups):
+        rg = md.row_group(g)
+        s0, s1 = rg.column(c0).statistics, rg.column(c1).statistics
+        ok = True
+        if s0 is not None and s0.has_min_max:
+            lo, hi = s0.min, s0.max
+            lo = lo.decode() if isinstance(lo, bytes) else lo
+            hi = hi.decode() if isinstance(hi, bytes) else hi
+            ok = lo <= record <= hi
+        if ok and s1 is not None and s1.has_min_max:
+            ok = s1.max > f1_gt and s1.min < f1_lt
+        if ok:
+            keep.append(g)
+    if stats is not None:
+        stats.update(row_groups=md.num_row_groups, row_groups_read=len(keep))
+    if not keep:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z.copy(), z.copy()
+    t = pf.read_row_groups(keep, columns=["f0", "f1", "f2", "f3"])
+    f1 = t.column("f1")
+    mask = pc.and_(pc.equal(t.column("f0"), record), pc.and_(pc.greater(f1, f1_gt), pc.less(f1, f1_lt)))
+    t = t.filter(mask)
     return (t.column("f1").to_numpy(), t.column("f2").to_numpy(), t.column("f3").to_numpy())

@@ -273,6 +273,25 @@ def format_membership(mat):
 
 
 # --------------------------------------------------------------------------
+# `memo view` binning (src/plot_conservation.py:46-58)
+# --------------------------------------------------------------------------
+def view_bins(vec, n_docs, n_bins):
+    """float64 [n_bins, n_docs + 1]: per bin, count(value) / bin size, bins cut at
+    int(linspace(0, positions, n_bins + 1)) (``plot_conservation.py:51-56``).  Raises
+    ZeroDivisionError on an empty bin like the reference."""
+    vec = [int(x) for x in vec]
+    positions = len(vec)
+    edges = list(map(int, np.linspace(0, positions, n_bins + 1)))
+    out = np.zeros((n_bins, n_docs + 1), dtype=np.float64)
+    for b, (lo, hi) in enumerate(zip(edges[:-1], edges[1:])):
+        chunk = vec[lo:hi]
+        total = len(chunk)
+        for order in range(n_docs + 1):
+            out[b, order] = chunk.count(order) / total
+    return out
+
+
+# --------------------------------------------------------------------------
 # synthetic HPRC-shaped DAP (SURVEY 8d).  Integer-only so that this numpy
 # form and the CUDA generator agree bit for bit.
 # --------------------------------------------------------------------------

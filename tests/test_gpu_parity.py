@@ -466,6 +466,33 @@ def test_index_stream_memory_is_bounded_by_the_chunk():
     assert np.array_equal(got[1][m], want_head[1][want_head[1] < 199_000])
 
 
+def test_view_bins_match_oracle(tmp_path):
+    """`memo view` binning kernel (plot_conservation.py:46-58) against the oracle, through the
+    API and through the drop-in's preprocess_data; uint8 and uint16 vectors, bins that do not
+    divide the window, more bins than a slice, values above -n."""
+    from memo_b200 import api, plot_conservation
+    rng = np.random.default_rng(6)
+    for n, n_docs, n_bins in ((20, 5, 4), (100_003, 10, 500), (300_000, 94, 7), (70_001, 400, 33), (5000, 3, 5000)):
+        vec = rng.integers(1, n_docs + 1, n)
+        vec[rng.random(n) < 0.7] = n_docs
+        if n == 20:
+            vec[3] = n_docs + 2                                # not in the table, still in the bin size
+        want = mo.view_bins(vec, n_docs, n_bins)
+        wide = n_docs > 255
+        dev = torch.from_numpy(vec.astype(np.int16 if wide else np.uint8)).cuda()
+        got = plot_conservation.bin_composition(dev, n_docs, n_bins)
+        assert np.array_equal(got, want), (n, n_docs, n_bins)
+        counts = api.view_bins(dev, n_docs, n_bins)
+        assert int(counts.sum()) == int((vec <= n_docs).sum())
+    path = tmp_path / "cons.txt"
+    path.write_text("\n".join(map(str, vec)) + "\n")
+    df = plot_conservation.preprocess_data(str(path), n_docs, n_bins)
+    assert df["value"].tolist() == want[:, :n_docs].T.reshape(-1).tolist()
+    assert df["bin"].tolist() == np.tile(np.arange(n_bins), n_docs).tolist()
+    with pytest.raises(ZeroDivisionError):
+        plot_conservation.bin_composition(dev[:3], n_docs, 10)
+
+
 def test_host_query_matches_oracle():
     from memo_b200 import host
     C, L = 9, 40000
@@ -509,6 +536,13 @@ def test_cli_round_trip_example(example_golden, tmp_path, capsysbinary):
         pq_path = tmp_path / f"{tag}.parquet"
         parquet_compress_bed.main(parquet_compress_bed.parse_arguments(["-f", str(bed), "-o", str(pq_path)]))
         capsysbinary.readouterr()
+        # extension: the Parquet index straight from the device columns (no BED text in between)
+        import pyarrow.parquet as pq
+        direct = tmp_path / f"{tag}_direct.parquet"
+        args = dap_to_bed.parse_arguments(argv + ["--parquet", str(direct)])
+        dap_to_bed.check_args(args)
+        dap_to_bed.main(args)
+        assert pq.read_table(direct).equals(pq.read_table(pq_path))
         for q in g["queries"]:
             if q["membership"] != (not order):
                 continue

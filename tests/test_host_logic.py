@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in memo_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.memo_abi_version() == 4
+    assert lib.memo_abi_version() == 5
 
 
 def test_struct_layouts_match_header():
@@ -267,3 +267,48 @@ def test_dap_text_empty_field_raises_like_int(tmp_path):
     p.write_text("0 3 5\n1 2 \n2 4 4\n")
     with pytest.raises(ValueError):
         io.read_dap_text(str(p))
+
+
+def test_parquet_row_groups_prune_the_query_read(tmp_path):
+    """the Parquet index is written in row groups cut at record changes with
+    min/max statistics (IndexParquetWriter) and read_index_rows reads only the groups a window
+    touches; rows, schema and codec are what parquet_compress_bed.py writes."""
+    from memo_b200 import io
+    rng = np.random.default_rng(0)
+    recs = ["chrA", "chrB", "chrC"]
+    cols = []
+    for r, n in zip(recs, (50000, 300, 70000)):
+        f1 = np.sort(rng.integers(1, 10 ** 6, n))
+        cols.append((np.full(n, recs.index(r)), f1, f1 + rng.integers(0, 500, n), rng.integers(1, 10, n)))
+    rec, f1, f2, f3 = (np.concatenate([c[i] for c in cols]) for i in range(4))
+    table = io.index_table([(r, 0) for r in recs], rec, f1, f2, f3)
+    path = tmp_path / "i.parquet"
+    with io.IndexParquetWriter(str(path), rows_per_group=8000) as w:
+        for a in range(0, table.num_rows, 3333):
+            w.write(table.slice(a, 3333))
+    back = pq.read_table(path)
+    assert back.equals(table) and back.schema.equals(io.INDEX_SCHEMA) and back.schema.metadata is None
+    md = pq.ParquetFile(path).metadata
+    assert md.num_row_groups >= 15 and md.row_group(0).column(0).compression == "ZSTD"
+    names = np.array(recs)[rec]
+    for name, a, b, most in (("chrA", 1000, 60000, 2), ("chrB", 0, 10 ** 6, 1), ("chrC", 500000, 500100, 2),
+                             ("nochr", 0, 5, 0)):
+        st = {}
+        g = io.read_index_rows(str(path), name, a, b, stats=st)
+        sel = (names == name) & (f1 > a) & (f1 < b)
+        assert np.array_equal(g[0], f1[sel]) and np.array_equal(g[1], f2[sel]) and np.array_equal(g[2], f3[sel])
+        assert st["row_groups_read"] <= most < st["row_groups"], (name, st)
+    # a file written by the reference's writer settings (one big group) still reads correctly
+    pq.write_table(table, tmp_path / "plain.parquet", compression="ZSTD")
+    g = io.read_index_rows(str(tmp_path / "plain.parquet"), "chrC", 500000, 500100)
+    sel = (names == "chrC") & (f1 > 500000) & (f1 < 500100)
+    assert np.array_equal(g[0], f1[sel])
+
+
+def test_parquet_compress_bed_empty_bed_raises_like_the_reference(tmp_path):
+    """An empty BED makes the reference crash (pyarrow: empty CSV; writer None at :39)."""
+    from memo_b200 import parquet_compress_bed
+    bed = tmp_path / "e.bed"
+    bed.write_text("")
+    with pytest.raises(Exception):
+        parquet_compress_bed.bed_to_parquet(str(bed), str(tmp_path / "e.parquet"))

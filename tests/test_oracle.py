@@ -113,3 +113,18 @@ def test_synth_is_valid_ms_and_chunk_invariant():
 def test_position_beyond_records_raises():
     with pytest.raises(Exception, match="beyond all intervals"):
         mo.index_build(np.ones((5, 2)), [("a", 3)], True)
+
+
+def test_view_bins_known_answers():
+    """`memo view` binning (src/plot_conservation.py:46-58): example of the walkthrough
+    (example/README.md: 20 positions, 4 bins, 5 genomes) by hand."""
+    vec = [5, 4, 5, 4, 3, 4, 4, 5, 5, 4, 5, 4, 3, 5, 3, 5, 4, 5, 4, 3]     # SURVEY A.4, k=3 ref_1:0-20
+    comp = mo.view_bins(vec, 5, 4)
+    assert comp.shape == (4, 6)
+    assert comp[0].tolist() == [0, 0, 0, 0.2, 0.4, 0.4]
+    assert comp[1].tolist() == [0, 0, 0, 0, 0.6, 0.4]
+    assert comp[3].tolist() == [0, 0, 0, 0.2, 0.4, 0.4]
+    assert np.allclose(comp.sum(axis=1), 1.0)
+    import pytest
+    with pytest.raises(ZeroDivisionError):
+        mo.view_bins([1, 2], 5, 4)

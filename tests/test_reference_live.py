@@ -112,3 +112,48 @@ def test_c_port_against_live_reference_at_scale(C, order, tmp_path):
     vals = np.concatenate([mo.synth_dap(n, C, seed=31 + i) for i, n in enumerate(lens)]).astype(np.int64)
     want = _run_reference_index(tmp_path, records, vals, order)
     assert _bed_text(records, co.index_build(vals, records, order)) == want
+
+
+def _reference_preprocess_data():
+    """src/plot_conservation.py's preprocess_data, imported from the unmodified file with a stub
+    standing in for plotnine (absent here; the function itself only needs numpy / pandas)."""
+    import importlib.util
+    import types
+    stub = types.ModuleType("plotnine")
+    for name in ("ggplot aes theme themes element_blank element_line element_text geom_bar ggtitle xlab ylab "
+                 "scale_y_continuous scale_fill_gradient").split():
+        setattr(stub, name, object())
+    opts = types.ModuleType("plotnine.options")
+    opts.figure_size = None
+    saved = {k: sys.modules.get(k) for k in ("plotnine", "plotnine.options")}
+    sys.modules["plotnine"], sys.modules["plotnine.options"] = stub, opts
+    try:
+        spec = importlib.util.spec_from_file_location("ref_plot_conservation", os.path.join(SRC, "plot_conservation.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.preprocess_data
+
+
+def test_oracle_view_bins_vs_live_reference(tmp_path):
+    """`memo view` binning: the oracle's view_bins against preprocess_data of the reference."""
+    ref = _reference_preprocess_data()
+    rng = np.random.default_rng(20240622)
+    for case in range(12):
+        n_docs = int(rng.integers(2, 12))
+        n = int(rng.integers(30, 400))
+        n_bins = int(rng.integers(1, 25))
+        vec = rng.integers(1, n_docs + 1, n)
+        vec[rng.random(n) < 0.6] = n_docs
+        path = tmp_path / f"cons{case}.txt"
+        path.write_text("\n".join(map(str, vec)) + "\n")
+        df = ref(str(path), n_docs, n_bins)
+        comp = mo.view_bins(vec, n_docs, n_bins)
+        assert df["bin"].tolist() == np.tile(np.arange(n_bins), n_docs).tolist()
+        assert df["No. Genomes"].tolist() == np.repeat(np.arange(n_docs, dtype=float), n_bins).tolist()
+        assert df["value"].tolist() == comp[:, :n_docs].T.reshape(-1).tolist(), case
