@@ -173,6 +173,17 @@ int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* 
                           int32_t n_docs, uint32_t* out_bits, int32_t* status,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same window answered for several k in ONE launch (BASELINE configs[4]: k = 15 .. 101):
+ * tile hand-out, row search and rows (L1/L2) are shared by the k values; src/memo_query.py
+ * :42-63 run once per k.  ks: HOST array of n_k (<= 16) values.  Result i (for ks[i]) starts
+ * at out + i * stride bytes: conservation (membership == 0, n_docs <= 255) uint8 [W] with
+ * stride = W rounded up to 16; membership uint32 [W, ceil(n_docs/32)] with stride = its size
+ * (W must then keep that a multiple of 16 bytes). */
+int memo_query_sweep(int32_t membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
+                     int64_t n_rows, int64_t q_start, int64_t q_end, const int32_t* ks, int32_t n_k,
+                     int32_t n_docs, void* out, int32_t* status, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Synthetic HPRC-shaped DAP (measurement only): fills rows
  * [row0, row0 + rows) of one record of length rec_len into dap[rows, ld].
  * Integer-only; bit-identical to oracle/memo_oracle.py:synth_dap.

@@ -51,6 +51,8 @@ SIGNATURES = {
                                           _vp, _vp, _sz, _vp]),
     "memo_query_membership": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
                                         _vp, _sz, _vp]),
+    "memo_query_sweep": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i64, _i64, C.POINTER(C.c_int32), _i32, _i32, _vp,
+                                   _vp, _vp, _sz, _vp]),
     "memo_synth_workspace_bytes": (_sz, [_i64, _i32]),
     "memo_synth_dap": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _u64, _i32, _vp, _sz, _vp]),
     "memo_format_workspace_bytes": (_sz, [_i64]),

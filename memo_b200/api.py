@@ -286,6 +286,42 @@ def query_membership(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_sta
     return out
 
 
+def query_sweep(f1: torch.Tensor, f2: torch.Tensor, f3: torch.Tensor, q_start: int, q_end: int,
+                ks: Sequence[int], n_docs: int, membership: bool = False,
+                workspace: Optional[torch.Tensor] = None, check: bool = True) -> torch.Tensor:
+    """The window [q_start, q_end) answered for every k of `ks` (BASELINE configs[4]: 15 .. 101) in
+    one launch per 16 values: conservation uint8 [len(ks), W16] (W16 = W rounded up to 16; row i =
+    the vector for ks[i] in its first W bytes) or membership int32-typed uint32 [len(ks), W, NW]."""
+    lib = _lib.load()
+    _query_common(f1, f2, f3)
+    dev = f1.device
+    W = max(0, q_end - q_start)
+    ks = [int(k) for k in ks]
+    if membership:
+        nw = (n_docs + 31) // 32
+        if (W * nw) % 4:
+            raise MemoError("membership sweep: W * ceil(n_docs / 32) must be a multiple of 4")
+        out = torch.empty((len(ks), W, nw), dtype=torch.int32, device=dev)
+    else:
+        out = torch.empty((len(ks), (W + 15) // 16 * 16), dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = lib.memo_query_workspace_bytes(W)
+    ws = workspace if workspace is not None and workspace.numel() >= need else \
+        torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    for a in range(0, len(ks), 16):
+        part = ks[a:a + 16]
+        arr = (C.c_int32 * len(part))(*part)
+        rc = lib.memo_query_sweep(1 if membership else 0, _ptr(f1), _ptr(f2), _ptr(f3), f1.numel(), q_start, q_end,
+                                  arr, len(part), n_docs, out[a].data_ptr() if W else 0, status.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(rc, "memo_query_sweep")
+        bad |= status
+    if check and int(bad.item()) != 0:
+        raise IndexError("index row order / genome id out of range for -n (the reference writes out of bounds)")
+    return out
+
+
 def unpack_membership(bits: np.ndarray, n_docs: int) -> np.ndarray:
     """uint32 [W, NW] -> uint8 [W, n_docs] (host helper for tests / writers)."""
     b = np.ascontiguousarray(bits).view(np.uint32)

@@ -54,8 +54,8 @@ size_t general_workspace_bytes(int64_t rows, int32_t n_cols, const memo_segment_
 size_t query_planes_workspace_bytes();
 int query_planes_max_membership_docs();
 int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
-                        int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs,
-                        void* out, int32_t* status, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream);
+                        int64_t n_rows, int64_t q_start, int64_t q_end, const int32_t* ks, int32_t n_k,
+                        int32_t n_docs, void* out, int64_t out_stride, int32_t* status, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace memo

@@ -208,7 +208,7 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     if (!out_u16 && q_end + k < (1ll << 31) - (1ll << 17) &&
         !(getenv("MEMO_QUERY_PLANES") && atoi(getenv("MEMO_QUERY_PLANES")) == 0) &&
         ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3)) & 15) == 0)
-        return launch_query_planes(0, f1, f2, f3, n_rows, q_start, q_end, k, n_docs, out, status, workspace,
+        return launch_query_planes(0, f1, f2, f3, n_rows, q_start, q_end, &k, 1, n_docs, out, 0, status, workspace,
                                    workspace_bytes, stream);
     // tiles of 8192 positions; dense indexes (many rows per position) get smaller tiles so
     // that the work per tile stays small against the number of tiles per CTA
@@ -237,6 +237,35 @@ int memo_query_conservation(const int32_t* f1, const uint32_t* f2, const int32_t
     return MEMO_OK;
 }
 
+int memo_query_sweep(int32_t membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
+                     int64_t n_rows, int64_t q_start, int64_t q_end, const int32_t* ks, int32_t n_k,
+                     int32_t n_docs, void* out, int32_t* status, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
+    using namespace memo;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MEMO_REQUIRE(q_end >= q_start && q_start >= 0, "bad window [%lld, %lld)", (long long)q_start, (long long)q_end);
+    MEMO_REQUIRE(ks != nullptr && n_k >= 1 && n_k <= 16, "1 .. 16 k values per sweep");
+    int32_t k_max = 1;
+    for (int i = 0; i < n_k; ++i) {
+        MEMO_REQUIRE(ks[i] >= 1, "k must be >= 1");
+        if (ks[i] > k_max) k_max = ks[i];
+    }
+    MEMO_REQUIRE(n_docs >= 1 && (membership ? n_docs <= query_planes_max_membership_docs() : n_docs <= 255),
+                 "n_docs = %d: the sweep runs on the bit-plane kernel only", n_docs);
+    MEMO_REQUIRE(n_rows >= 0 && status != nullptr, "bad rows/status");
+    MEMO_REQUIRE(q_end + k_max < (1ll << 31) - (1ll << 17), "window too far for 32-bit tile arithmetic");
+    const long long W = q_end - q_start;
+    MEMO_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), stream));
+    if (W == 0) return MEMO_OK;
+    MEMO_REQUIRE(out != nullptr, "out must not be NULL");
+    const int64_t stride = membership ? (int64_t)W * 4 * ((n_docs + 31) / 32) : (int64_t)((W + 15) / 16 * 16);
+    MEMO_REQUIRE(((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3) |
+                   reinterpret_cast<uintptr_t>(out) | (uintptr_t)stride) & 15) == 0,
+                 "rows and results must be 16-byte aligned");
+    return launch_query_planes(membership, f1, f2, f3, n_rows, q_start, q_end, ks, n_k, n_docs, out, stride, status,
+                               workspace, workspace_bytes, stream);
+}
+
 int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* f3,
                           int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k,
                           int32_t n_docs, uint32_t* out_bits, int32_t* status, void* workspace,
@@ -260,7 +289,7 @@ int memo_query_membership(const int32_t* f1, const uint32_t* f2, const int32_t* 
         ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(f3) |
           reinterpret_cast<uintptr_t>(out_bits)) & 15) == 0 &&
         !(getenv("MEMO_QUERY_PLANES") && atoi(getenv("MEMO_QUERY_PLANES")) == 0))
-        return launch_query_planes(1, f1, f2, f3, n_rows, q_start, q_end, k, n_docs, out_bits, status, workspace,
+        return launch_query_planes(1, f1, f2, f3, n_rows, q_start, q_end, &k, 1, n_docs, out_bits, 0, status, workspace,
                                    workspace_bytes, stream);
     const int TP = QM_WORDS / NW;
     const long long n_tiles = (W + TP - 1) / TP;

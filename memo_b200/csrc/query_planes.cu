@@ -31,6 +31,8 @@
 // workspace, so that no single warp decides the kernel's time.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace memo {
@@ -50,7 +52,10 @@ struct PlaneParams {
     const uint32_t* f2;
     const int32_t* f3;
     long long n_rows, s, W;
-    int k, n_docs;
+    int n_docs;
+    int n_k;                       // k values answered by this launch (a sweep shares the tile hand-out,
+    int ks[16];                    //  the row search and the rows in L1/L2); result i at out + i * out_stride
+    long long out_stride;          // bytes between the results of consecutive k values
     int NOP;                       // planes per tile: n_docs rounded up to a multiple of the group size
     int WPT;                       // words per plane
     int TP;                        // positions per tile = 32 WPT
@@ -122,8 +127,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
     uint32_t* const planes = smem[threadIdx.x >> 5];
     const int WPT = P.WPT, n_docs = P.n_docs;
     const int n_words = P.NOP * WPT;
-    const uint32_t km1 = (uint32_t)(P.k - 1);
-    const int halo = (P.k > 2 ? P.k : 2) - 2;        // rows starting up to tile end + halo can cover
+    uint32_t km1 = 0;                                // k - 1 of the k value being answered
+    int halo = 0;                                    // rows starting up to tile end + halo can cover
+    unsigned char* out_k = static_cast<unsigned char*>(P.out);
     const long long n_rows = P.n_rows;
 
     // One tile: window positions [t0, t0 + tn), rows from r on (the first row with f1 > s + t0).
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
             //      group above, which is done with); then the words go out in position order.
             const int NW = P.NOP >> 5;
             const uint32_t last_mask = (n_docs & 31) ? ((1u << (n_docs & 31)) - 1u) : 0xFFFFFFFFu;
-            uint32_t* const ob = static_cast<uint32_t*>(P.out) + t0 * NW;
+            uint32_t* const ob = reinterpret_cast<uint32_t*>(out_k) + t0 * NW;
             const bool act = lane < WPT && 32 * lane < tn;
             for (int g = NW - 1; g >= 0; --g) {
                 uint32_t* const reg = planes + 32 * g * WPT;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 }
                 w[j] = acc;
             }
-            uint8_t* const o = static_cast<uint8_t*>(P.out) + t0 + 32 * wc;
+            uint8_t* const o = out_k + t0 + 32 * wc;
             if (32 * wc + 32 <= tn) {
                 reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -404,7 +410,17 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
                 continue;
             }
         }
-        const long long r_next = do_tile(t0, tn, r, true);
+        // every k of the sweep over the same tile and rows (a heavy tile is handed on at the first
+        // k: its pieces answer all of them)
+        long long r_next = -1;
+        for (int ki = 0; ki < P.n_k; ++ki) {
+            const int k = P.ks[ki];
+            km1 = (uint32_t)(k - 1);
+            halo = (k > 2 ? k : 2) - 2;
+            out_k = static_cast<unsigned char*>(P.out) + (long long)ki * P.out_stride;
+            r_next = do_tile(t0, tn, r, ki == 0);
+            if (r_next < 0) break;
+        }
         if (from_run) {
             r_run = r_next;
             ++t_cur;
@@ -422,13 +438,17 @@ size_t query_planes_workspace_bytes() { return QP_WS_HEADER + sizeof(HeavyTile) 
 int query_planes_max_membership_docs() { return QP_WORDS_M; }
 
 int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, const int32_t* f3,
-                        int64_t n_rows, int64_t q_start, int64_t q_end, int32_t k, int32_t n_docs,
-                        void* out, int32_t* status, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream) {
+                        int64_t n_rows, int64_t q_start, int64_t q_end, const int32_t* ks, int32_t n_k,
+                        int32_t n_docs, void* out, int64_t out_stride, int32_t* status, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
     PlaneParams P;
     P.f1 = f1; P.f2 = f2; P.f3 = f3;
     P.n_rows = n_rows; P.s = q_start; P.W = q_end - q_start;
-    P.k = k; P.n_docs = n_docs;
+    P.n_docs = n_docs;
+    MEMO_REQUIRE(n_k >= 1 && n_k <= 16, "1 .. 16 k values per launch");
+    P.n_k = n_k;
+    for (int i = 0; i < 16; ++i) P.ks[i] = i < n_k ? ks[i] : 0;
+    P.out_stride = out_stride;
     int wpt;
     if (membership) {
         P.NOP = (n_docs + 31) / 32 * 32;                 // groups of 32 genomes = output words
@@ -454,7 +474,9 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     P.heavy_rows = QP_HEAVY;
     if (P.n_tiles > 0 && 3 * (n_rows / P.n_tiles) > P.heavy_rows)
         P.heavy_rows = (int)min(3 * (n_rows / P.n_tiles), (long long)(1 << 30)) / 128 * 128;
-    if (const char* e = getenv("MEMO_QUERY_HEAVY")) P.heavy_rows = atoi(e) / 128 * 128;   // tuning: 0 = never
+    static const int env_heavy = getenv("MEMO_QUERY_HEAVY") ? atoi(getenv("MEMO_QUERY_HEAVY")) : -1;   // tuning: 0 = never
+    static const int env_run = getenv("MEMO_QUERY_RUN") ? atoi(getenv("MEMO_QUERY_RUN")) : 0;
+    if (env_heavy >= 0) P.heavy_rows = env_heavy / 128 * 128;
     const size_t need = query_planes_workspace_bytes();
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("workspace too small: %zu < %zu", workspace_bytes, need);
@@ -475,19 +497,30 @@ int launch_query_planes(int membership, const int32_t* f1, const uint32_t* f2, c
     else if (bits <= 6) { fn = query_planes_kernel<6, 8, false>; slot = 3; }
     else if (bits <= 7) { fn = query_planes_kernel<7, 8, false>; slot = 4; }
     else { fn = query_planes_kernel<8, 8, false>; slot = 5; }
-    static int per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (per_sm[slot] == 0) {
-        int n = 0;
-        MEMO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, QP_WARPS * 32, 0));
-        per_sm[slot] = n > 0 ? n : 1;
+    // resident CTAs per SM of the variant on the current device (one query per device and variant)
+    int ctas = 0;
+    {
+        static std::mutex mu;
+        static int per_sm[64][7];
+        int dev = 0;
+        MEMO_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || per_sm[dev][slot] == 0) {
+            int n = 0;
+            MEMO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, QP_WARPS * 32, 0));
+            ctas = n > 0 ? n : 1;
+            if (dev >= 0 && dev < 64) per_sm[dev][slot] = ctas;
+        } else {
+            ctas = per_sm[dev][slot];
+        }
     }
-    const long long warps = (long long)device_sm_count() * per_sm[slot] * QP_WARPS;
+    const long long warps = (long long)device_sm_count() * ctas * QP_WARPS;
     // runs of consecutive tiles share one row search; about 3 runs per warp keep the tail short
     long long run = P.n_tiles / (warps * 3);
     P.run = (int)(run < 1 ? 1 : run > 16 ? 16 : run);
-    if (const char* e = getenv("MEMO_QUERY_RUN")) P.run = atoi(e) > 0 ? atoi(e) : P.run;     // tuning
+    if (env_run > 0) P.run = env_run;                // tuning
     P.n_runs = (P.n_tiles + P.run - 1) / P.run;
-    long long grid = (long long)device_sm_count() * per_sm[slot];
+    long long grid = (long long)device_sm_count() * ctas;
     const long long enough = (P.n_runs + QP_WARPS - 1) / QP_WARPS;
     if (grid > enough) grid = enough;
     fn<<<(unsigned)grid, QP_WARPS * 32, 0, stream>>>(P);

@@ -496,14 +496,15 @@ def _rows_to_device(f1, f2, f3, dev, trusted=False):
         cols.append(t if t is not None and t.is_pinned() else None)
     if all(c is not None for c in cols):              # rows straight from build_index: already pinned
         return tuple(c.to(dev, non_blocking=True) for c in cols)
-    stage = _pinned("qrows", 12 * n)[:12 * n].view(torch.int32).view(3, n)
+    n4 = (n + 3) // 4 * 4                             # columns 16-byte aligned on the device
+    stage = _pinned("qrows", 12 * n4)[:12 * n4].view(torch.int32).view(3, n4)
     view = stage.numpy()
-    view[0] = f1                                      # same-kind casts into the pinned block
-    view[1] = f2.astype(np.uint32, copy=False).view(np.int32) if f2.dtype != np.int32 else f2
-    view[2] = f3
+    view[0, :n] = f1                                  # same-kind casts into the pinned block
+    view[1, :n] = f2.astype(np.uint32, copy=False).view(np.int32) if f2.dtype != np.int32 else f2
+    view[2, :n] = f3
     d = stage.to(dev, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()      # the staging block is reused by the next call
-    return d[0], d[1], d[2]
+    return d[0, :n], d[1, :n], d[2, :n]
 
 
 def query(f1, f2, f3, q_start: int, q_end: int, k: int, n_docs: int, membership: bool,
@@ -538,15 +539,25 @@ def query(f1, f2, f3, q_start: int, q_end: int, k: int, n_docs: int, membership:
 
 def query_sweep(f1, f2, f3, q_start: int, q_end: int, ks: Sequence[int], n_docs: int, membership: bool,
                 device=None, trusted: bool = False) -> dict:
-    """The same window queried for several k (BASELINE configs[4]: k = 15 .. 101): the index
-    rows go to the device once, every k is one query launch over them.  Returns {k: result}
-    with the results of `query` (conservation: uint8/uint16 numpy vectors; membership: uint8
-    [W, n_docs] matrices)."""
+    """The same window queried for several k (BASELINE configs[4]: k = 15 .. 101): the index rows
+    go to the device once and all k are answered by ONE launch per 16 values (memo_query_sweep:
+    tiles, row search and rows shared) and one copy back.  Returns {k: result} with the results
+    of `query` (conservation: uint8 numpy vectors; membership: uint8 [W, n_docs] matrices).
+    More than 255 genomes (uint16 results) take one launch per k."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if q_end < q_start:
         raise ValueError("negative dimensions are not allowed")
     t1, t2, t3 = _rows_to_device(f1, f2, f3, dev, trusted)
     W = q_end - q_start
+    ks = list(ks)
+    nw = (n_docs + 31) // 32
+    fused = (n_docs <= 255 if not membership else (W * nw) % 4 == 0) and \
+        q_end + max(ks, default=1) < 2**31 - 2**17 and all(t.data_ptr() % 16 == 0 for t in (t1, t2, t3))
+    if fused:
+        out = api.query_sweep(t1, t2, t3, q_start, q_end, ks, n_docs, membership).cpu().numpy()
+        if membership:
+            return {k: api.unpack_membership(out[i], n_docs) for i, k in enumerate(ks)}
+        return {k: out[i, :W] for i, k in enumerate(ks)}
     ws = torch.empty(max(api._lib.load().memo_query_workspace_bytes(W), 1), dtype=torch.uint8, device=dev)
     res = {}
     for k in ks:

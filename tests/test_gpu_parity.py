@@ -344,6 +344,28 @@ def test_query_position_shards_and_k_sweep(C, membership):
             assert np.array_equal(np.concatenate(parts[k]), whole[k]), (world, k)
 
 
+@pytest.mark.parametrize("C,membership", [(9, False), (93, False), (93, True)])
+def test_query_sweep_one_launch_many_k(C, membership):
+    """memo_query_sweep: 20 k values (two launches of <= 16) incl. k = 1, 2 and a window whose
+    start is the dense start of the record (heavy tiles handed on in pieces answer every k),
+    against the oracle per k; unaligned window length."""
+    api = _api()
+    L = 120_000
+    vals = mo.synth_dap(L, C, seed=5 * C + 2)
+    _, s, e, c = mo.index_build(vals, [("chrK", L)], not membership)
+    n_docs = C + 1
+    f1 = torch.from_numpy(s.astype(np.int32)).cuda()
+    f2 = torch.from_numpy(e.astype(np.uint32).view(np.int32)).cuda()
+    f3 = torch.from_numpy(c.astype(np.int32)).cuda()
+    ks = [1, 2, 3, 15, 16, 17, 21, 31, 32, 33, 41, 51, 61, 64, 65, 71, 81, 91, 101, 129]
+    lo, hi = 0, (L - 1000 if membership else L - 1003)
+    out = api.query_sweep(f1, f2, f3, lo, hi, ks, n_docs, membership).cpu().numpy()
+    for i, k in enumerate(ks):
+        want = mo.query(s, e, c, lo, hi, k, n_docs, membership)
+        got = api.unpack_membership(out[i], n_docs) if membership else out[i, :hi - lo].astype(np.int64)
+        assert np.array_equal(got, want), k
+
+
 def test_query_order_out_of_range_raises():
     s = np.array([5, 9]); e = np.array([9, 12]); c = np.array([1, 7])
     with pytest.raises(IndexError):
