@@ -216,14 +216,15 @@ class Workload:
     """One record of `rec_len` rows x C columns, position-sharded over the ranks;
     this rank's shard resident on its device, outputs sized by a counting run."""
 
-    def __init__(self, rec_len, C, k, membership, seed, rank, world, dev, tuning):
+    def __init__(self, rec_len, C, k, membership, seed, rank, world, dev, tuning, span=None):
         import torch
         from memo_b200 import api, shard, _lib
         self.torch, self.api = torch, api
         self.rec_len, self.C, self.k, self.membership = rec_len, C, k, membership
         self.n_docs = C + 1
         self.rank, self.world, self.dev, self.tuning, self.seed = rank, world, dev, tuning, seed
-        self.lo, self.hi = shard.shard_range(rec_len, world, rank)
+        # the rank's position shard of the record, or an explicit span of it (whole-genome mode)
+        self.lo, self.hi = shard.shard_range(rec_len, world, rank) if span is None else span
         self.Lr = self.hi - self.lo
         self.buf_lo = self.lo - 1 if self.lo > 0 else self.lo      # 1-row left halo
         self.buf_hi = min(self.hi + KH, rec_len)                   # right halo for the query
@@ -536,6 +537,117 @@ def extra_config(name, rec_len, C, membership, seed, k, dev, steps, peak, peak_s
                                           "note": "query timed alone, 512 MB written between launches"}}
 
 
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+          138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+          83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+WG_KS = [15, 21, 31, 41, 51, 61, 71, 81, 91, 101]
+
+
+def run_whole_genome(args, rank, world, local, dev, barrier):
+    """BASELINE configs[4]: 94 genomes x the 24 GRCh38 primary records (3 088 269 832 bp), the
+    concatenated pivot cut into one position range per GPU; index build + k sweep (15 .. 101,
+    one fused launch).  1.15 TB of DAP does not fit the GPUs at once: every rank walks its range
+    in pieces of one record and at most --wg-piece-rows rows, generated on the device (untimed),
+    built and queried with the piece resident (timed with CUDA events); times add up per rank,
+    the slowest rank decides."""
+    import torch
+    import torch.distributed as dist
+    from memo_b200 import api, shard, _lib
+    C, ks = args.cols, WG_KS
+    n_docs = C + 1
+    lens = [max(1000, int(n * args.wg_scale)) for n in GRCH38]     # (--wg-scale < 1: smoke runs only)
+    total = sum(lens)
+    g_lo, g_hi = shard.shard_range(total, world, rank)
+    pieces, acc = [], 0
+    for rid, n in enumerate(lens):
+        a, b = max(g_lo, acc), min(g_hi, acc + n)
+        while a < b:
+            e = min(b, a + args.wg_piece_rows)
+            pieces.append((rid, n, a - acc, e - acc))
+            a = e
+        acc += n
+    lib = _lib.load()
+    peak, peak_src = load_peaks()
+    t_idx = t_qry = t_kern = 0.0
+    n_rows = bytes_idx = bytes_q = 0
+    bp = 0
+    for rid, rec_len, lo, hi in pieces:
+        wl = Workload(rec_len, C, 31, False, SEED0 + 4 + rid, 0, 1, dev, {}, span=(lo, hi))
+        n, o = wl.n_all, wl.out
+        sweep = lambda: api.query_sweep(o[0][:n], o[1][:n], o[2][:n], lo, hi, ks, n_docs, False,
+                                        workspace=wl.q_ws, check=False)
+        wl.build()
+        res = sweep()                                     # warm-up + the result that is checked
+        torch.cuda.synchronize()
+        off = wl.lo - wl.buf_lo
+        for i, k in enumerate(ks):                        # conservation == 1 + #{MS >= k}, every k
+            for a in range(0, wl.Lr, 4_000_000):
+                b = min(a + 4_000_000, wl.Lr)
+                want = (1 + (wl.dap[off + a:off + b] >= k).sum(dim=1)).to(torch.uint8)
+                assert torch.equal(res[i, a:b], want), f"sweep result violates the invariant at k={k}"
+        del res
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        lib.memo_profile_enable(1)
+        reps = args.wg_reps
+        for _ in range(reps):
+            ev[0].record()
+            wl.build()
+            ev[1].record()
+            r = sweep()
+            ev[2].record()
+            torch.cuda.synchronize()
+            t_idx += ev[0].elapsed_time(ev[1]) / reps
+            t_qry += ev[1].elapsed_time(ev[2]) / reps
+            del r
+        lib.memo_profile_enable(0)
+        k_ms, k_n = ctypes.c_double(0.0), ctypes.c_int32(0)
+        _lib.check(lib.memo_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)), "memo_profile_collect")
+        t_kern += k_ms.value / max(k_n.value, 1)
+        owned = int(wl.seg_out_end[0].item())
+        n_rows += owned
+        bytes_idx += 4.0 * wl.Lr * C + 12.0 * owned
+        bytes_q += 12.0 * n + float(len(ks)) * wl.Lr      # SURVEY 8d: 12 n_in + K W
+        bp += wl.Lr
+        del wl, o
+        torch.cuda.empty_cache()
+    stats = torch.tensor([t_idx, t_qry, t_kern, t_idx + t_qry, float(n_rows), bytes_idx, bytes_q, float(bp)],
+                         dtype=torch.float64, device=dev)
+    mx, sm = stats.clone(), stats.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        t_i, t_q, t_k, t_all = (mx[i].item() for i in range(4))
+        line = {
+            "metric": "pivot bp/s (conservation index build + k-mer query sweep, k = 15 .. 101)",
+            "value": sm[7].item() / (t_all * 1e-3), "unit": "bp/s", "n_gpus": world,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: whole genome (24 GRCh38 primary records, {total} bp "
+                                   f"pivot{'' if args.wg_scale == 1 else ', lengths scaled by %g' % args.wg_scale}) x {n_docs} genomes, conservation index build + multi-k query sweep "
+                                   f"k = {ks} (one fused launch per piece), position ranges x{world}",
+                       "genomes": n_docs, "pivot_bp": total, "ks": ks, "pieces_rank0": len(pieces),
+                       "piece_rows_max": args.wg_piece_rows, "reps_per_piece": args.wg_reps,
+                       "timing": "per piece: device-resident DAP, CUDA events around build and sweep; generation "
+                                 "untimed; per-rank sums, max over ranks"},
+            "ms_total": t_all, "index_ms": t_i, "query_ms": t_q,
+            "index_bp_per_s": sm[7].item() / (t_i * 1e-3), "query_bp_per_s": sm[7].item() / (t_q * 1e-3),
+            "index_rows": int(sm[4].item()),
+            # aggregate bytes of all ranks / slowest rank's time, against N x the per-GPU peak
+            "roofline_index_build": {"bound": "hbm", "achieved": sm[5].item() / (t_i * 1e-3) / 1e9,
+                                     "peak": peak * world, "unit": "GB/s",
+                                     "frac": sm[5].item() / (t_i * 1e-3) / 1e9 / (peak * world),
+                                     "algorithmic_bytes": sm[5].item(), "peak_source": peak_src},
+            "roofline": {"kernel": "wide_kernel (streaming kernel of the build)", "bound": "hbm",
+                         "achieved": sm[5].item() / (t_k * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": sm[5].item() / (t_k * 1e-3) / 1e9 / (peak * world), "traffic": None},
+            "roofline_query": {"kernel": "query_planes_kernel, 10 k values per launch", "bound": "hbm",
+                               "achieved": sm[6].item() / (t_q * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                               "frac": sm[6].item() / (t_q * 1e-3) / 1e9 / (peak * world),
+                               "algorithmic_bytes": sm[6].item()},
+        }
+        print(json.dumps(line))
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -563,6 +675,11 @@ def main():
     ap.add_argument("--membership", action="store_true",
                     help="membership index (-m: no --order) + membership query (BASELINE configs[2])")
     ap.add_argument("--env", action="append", default=[], help="KEY=VAL set before the library loads (tuning)")
+    ap.add_argument("--wg", action="store_true",
+                    help="BASELINE configs[4]: whole genome (24 GRCh38 records) x 94, index build + k sweep")
+    ap.add_argument("--wg-piece-rows", type=int, default=64_000_000)
+    ap.add_argument("--wg-reps", type=int, default=2)
+    ap.add_argument("--wg-scale", type=float, default=1.0, help="scale the record lengths (smoke runs)")
     args = ap.parse_args()
     for kv in args.env:
         key, _, val = kv.partition("=")
@@ -593,6 +710,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.wg:
+        run_whole_genome(args, rank, world, local, dev, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     tuning = dict(rows_per_tile=args.rows_per_tile, emit_buf_records=args.emit_buf,
                   warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, stages=args.stages,
                   kernel_variant=args.variant)
