@@ -464,6 +464,19 @@ def e2e_leg(wl, args, barrier):
     if wl.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # what the host can feed at this rank count, with nothing else going on: plain pinned -> device
+    # copies of the same buffer on every rank at once (the ceiling the e2e figure runs against)
+    probe = torch.empty(host_dap.numel() // 2, dtype=torch.int32, device=wl.dev)
+    flat = host_dap.view(-1)[:probe.numel()]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        probe.copy_(flat, non_blocking=True)
+    torch.cuda.synchronize()
+    if wl.world > 1:
+        dist.barrier()
+    h2d_ceiling = 4 * probe.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    del probe
     # same rows as the device-resident path (the slice's rows are a prefix of the shard's)
     s, e, o = wl.owned_rows_between(sl_lo, sl_hi if not ends_record else wl.rec_len + 1)
     if not wl.membership:
@@ -477,9 +490,44 @@ def e2e_leg(wl, args, barrier):
             "steps": args.e2e_steps, "ms_per_step": 1e3 * t.item() / args.e2e_steps,
             "pivot_bp_per_gpu": n,
             "h2d_gbs_per_gpu": host_dap.numel() * 4 * args.e2e_steps / t.item() / 1e9,
+            "h2d_ceiling_gbs_per_gpu": h2d_ceiling,
             "note": f"host.build_index + host.query on the first {n} positions of every shard: pinned host DAP "
                     "streamed to the device in chunks overlapped with the build, index rows (12 B each) and "
-                    "the query result copied back to host; wall clock, max over ranks"}
+                    "the query result copied back to host; wall clock, max over ranks.  h2d_ceiling = plain "
+                    "pinned -> device copies on all ranks at once (what the host can feed: the e2e figure "
+                    "is bound by it, not by a collective)"}
+
+
+def e2e_text_leg(wl, args):
+    """The drop-in proper, from text: a dap.txt slice of the workload through
+    memo_b200.dap_to_bed (pyarrow CSV parse -> pinned chunks -> device build -> BED text), wall
+    clock.  The host text parse bounds it, which is why the figure is reported."""
+    import tempfile
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    from memo_b200 import dap_to_bed
+    n = min(wl.Lr, args.e2e_text_rows)
+    vals = wl.dap[:n].cpu().numpy()
+    with tempfile.TemporaryDirectory() as d:
+        dap, fai, bed = (os.path.join(d, f) for f in ("dap.txt", "p.fa.fai", "out.bed"))
+        cols = [pa.array(np.arange(n, dtype=np.int64))] + [pa.array(vals[:, j]) for j in range(wl.C)]
+        pacsv.write_csv(pa.table(cols, names=[f"f{i}" for i in range(wl.C + 1)]), dap,
+                        write_options=pacsv.WriteOptions(include_header=False, delimiter=" "))
+        with open(fai, "w") as fh:
+            fh.write(f"chrS\t{wl.rec_len}\t6\t{wl.rec_len}\t{wl.rec_len + 1}\n")
+        argv = ["--mem", "--overlap", "--fai", fai, "--dap", dap, "--out", bed] + (["--order"] if wl.order else [])
+        a = dap_to_bed.parse_arguments(argv)
+        dap_to_bed.check_args(a)
+        dap_to_bed.main(a)                                 # (first call: pinned buffers get allocated)
+        t0 = time.perf_counter()
+        dap_to_bed.main(a)
+        dt = time.perf_counter() - t0
+        size, out_size = os.path.getsize(dap), os.path.getsize(bed)
+    return {"value": n / dt, "unit": "bp/s", "rows": n, "seconds": dt, "dap_txt_bytes": size, "bed_bytes": out_size,
+            "text_gbs": size / dt / 1e9,
+            "note": "python -m memo_b200.dap_to_bed on a dap.txt slice of the workload, in process, wall clock: "
+                    "multi-threaded pyarrow CSV parse -> streaming device build -> BED text"}
 
 
 def cpu_leg(wl, args):
@@ -660,6 +708,7 @@ def main():
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-rows", type=int, default=16_000_000, help="host-resident slice per GPU of the e2e leg")
+    ap.add_argument("--e2e-text-rows", type=int, default=1_000_000, help="rows of the dap.txt slice of the e2e_text figure")
     ap.add_argument("--ref-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--parity-rows", type=int, default=1_000_000, help="positions either side of a shard cut compared with the port")
@@ -739,6 +788,9 @@ def main():
         ok, m = shard_parity(wl, args)
         parity = {"ok": ok, "positions_each_side": m, "cuts": world - 1}
     e2e = None if (args.no_e2e or args.membership) else e2e_leg(wl, args, barrier)
+    e2e_text = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.membership:
+        e2e_text = e2e_text_leg(wl, args)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_leg(wl, args)
@@ -761,7 +813,7 @@ def main():
             "index_rows": n_owned_total, "rho_cell": n_owned_total / (args.rows * args.cols),
             "index_rows_parked_rank0": t["parked_rows"],
             **r,
-            "cpu_baseline": cpu, "e2e": e2e,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_text": e2e_text,
             "shard_parity": None if parity is None else parity["ok"], "shard_parity_detail": parity,
             "gpu_launches": launches, "clocks": t["clocks"],
         }
