@@ -500,8 +500,8 @@ def e2e_leg(wl, args, barrier):
 
 def e2e_text_leg(wl, args):
     """The drop-in proper, from text: a dap.txt slice of the workload through
-    memo_b200.dap_to_bed (pyarrow CSV parse -> pinned chunks -> device build -> BED text), wall
-    clock.  The host text parse bounds it, which is why the figure is reported."""
+    memo_b200.dap_to_bed (file bytes -> pinned blocks -> device text parse -> device build ->
+    BED text), wall clock."""
     import tempfile
     import numpy as np
     import pyarrow as pa
@@ -527,7 +527,9 @@ def e2e_text_leg(wl, args):
     return {"value": n / dt, "unit": "bp/s", "rows": n, "seconds": dt, "dap_txt_bytes": size, "bed_bytes": out_size,
             "text_gbs": size / dt / 1e9,
             "note": "python -m memo_b200.dap_to_bed on a dap.txt slice of the workload, in process, wall clock: "
-                    "multi-threaded pyarrow CSV parse -> streaming device build -> BED text"}
+                    "file bytes -> pinned blocks -> device text parse (memo_dap_text_parse) -> streaming device "
+                    "build -> BED text (pyarrow); the reference's dap_to_bed.py runs this at 32 kbp/s on one core "
+                    "(BASELINE.md 2b)"}
 
 
 def cpu_leg(wl, args):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 5
+#define MEMO_B200_ABI_VERSION 6
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -205,6 +205,22 @@ int memo_format_conservation(const void* vals, int32_t is_u16, int64_t n, char* 
                              void* stream);
 int memo_format_membership(const uint32_t* bits, int64_t W, int32_t n_docs, char* out_text,
                            void* stream);
+
+/* dap.txt text -> DAP rows on the device.  Replaces the reference's line reader and row parse,
+ * src/dap_to_bed.py read_file :14-18 and get_new_record :85-88 (`map(int, row.split(' '))`).
+ *  text       device bytes [n_bytes] of WHOLE lines "pos v1 .. vC\n" (index.sh:83), 16-byte
+ *             aligned, readable up to the next multiple of 32 bytes
+ *  pos_first  the position the first line must carry; positions must be consecutive
+ *  out        device int32 [max_rows, ld]: row i = the n_cols lengths of line i
+ *  result     device int64 [4]: [0] lines parsed, [1] error bits: 1 = a character that is no
+ *             digit / space / newline, or an empty field (int() raises in the reference);
+ *             2 = a line with another number of fields; 4 = positions not consecutive;
+ *             8 = value >= 2^31; 16 = more than max_rows lines
+ *  workspace  memo_dap_text_workspace_bytes(n_bytes) */
+size_t memo_dap_text_workspace_bytes(int64_t n_bytes);
+int memo_dap_text_parse(const uint8_t* text, int64_t n_bytes, int32_t n_cols, int64_t pos_first,
+                        int32_t* out, int64_t max_rows, int32_t ld, int64_t* result,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* `memo view` binning.  Replaces src/plot_conservation.py preprocess_data :46-58: per
  * position bin, the number of positions holding each conservation value 0 .. n_docs.

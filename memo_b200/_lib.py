@@ -58,6 +58,8 @@ SIGNATURES = {
     "memo_format_workspace_bytes": (_sz, [_i64]),
     "memo_format_conservation": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "memo_format_membership": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "memo_dap_text_workspace_bytes": (_sz, [_i64]),
+    "memo_dap_text_parse": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "memo_view_bins": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 

@@ -364,6 +364,52 @@ def format_membership(bits: torch.Tensor, n_docs: int) -> bytes:
 
 
 # --------------------------------------------------------------------------
+# dap.txt text on the device
+# --------------------------------------------------------------------------
+class DapTextParser:
+    """dap.txt bytes -> int32 DAP rows on the device (memo_dap_text_parse; replaces the line
+    reader and `map(int, row.split(' '))` of src/dap_to_bed.py:14-18,85-88).  Reusable: keeps
+    its device buffers (text, rows, workspace) sized for `block_bytes` of text."""
+
+    ERRORS = ((1, ValueError, "invalid literal for int() in dap.txt (a character that is no digit, single "
+                              "space or newline, or an empty field)"),
+              (2, MemoError, "dap.txt: a line with another number of fields than the first line"),
+              (4, MemoError, "dap.txt positions are not consecutive (expected `nl -v0` numbering)"),
+              (8, MemoError, "DAP lengths must be in [0, 2^31)"),
+              (16, MemoError, "dap.txt: more lines in a block than its size allows"))
+
+    def __init__(self, n_cols: int, block_bytes: int, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise MemoError("no CUDA device: memo_b200 has no CPU fallback")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.C, self.block_bytes = n_cols, int(block_bytes)
+        self.text = torch.empty(self.block_bytes + 64, dtype=torch.uint8, device=self.dev)
+        # a line has at least 2 bytes per field ("0 ")
+        self.max_rows = self.block_bytes // (2 * (n_cols + 1)) + 2
+        self.rows = torch.empty((self.max_rows, n_cols), dtype=torch.int32, device=self.dev)
+        self.result = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        self.ws = torch.empty(max(self.lib.memo_dap_text_workspace_bytes(self.block_bytes), 1), dtype=torch.uint8,
+                              device=self.dev)
+
+    def parse(self, host_bytes: torch.Tensor, n_bytes: int, pos_first: int) -> torch.Tensor:
+        """host_bytes: pinned uint8 tensor holding n_bytes of WHOLE lines.  Returns the device
+        rows int32 [n_lines, C] (a view of this parser's buffer: valid until the next parse)."""
+        if n_bytes > self.block_bytes:
+            raise MemoError("text block larger than the parser was sized for")
+        self.text[:n_bytes].copy_(host_bytes[:n_bytes], non_blocking=True)
+        rc = self.lib.memo_dap_text_parse(self.text.data_ptr(), n_bytes, self.C, pos_first, self.rows.data_ptr(),
+                                          self.max_rows, self.C, self.result.data_ptr(), self.ws.data_ptr(),
+                                          self.ws.numel(), _stream_ptr(self.dev))
+        _lib.check(rc, "memo_dap_text_parse")
+        n_lines, err = self.result[:2].tolist()             # synchronises
+        for bit, exc, msg in self.ERRORS:
+            if err & bit:
+                raise exc(msg)
+        return self.rows[:n_lines]
+
+
+# --------------------------------------------------------------------------
 # view binning
 # --------------------------------------------------------------------------
 def view_bin_edges(n_positions: int, n_bins: int) -> np.ndarray:

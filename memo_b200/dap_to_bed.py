@@ -72,13 +72,19 @@ def check_args(args):
         raise Exception("Error: --parquet is a single-process output of its own (no --gpus, no --out).")
 
 
-def dap_blocks(args):
+def dap_blocks(args, byte_range=None):
     """(first position, iterator of int32 [n, C] blocks of consecutive DAP rows): the input is
-    streamed like the reference streams it (src/dap_to_bed.py:14-18), never held as a whole."""
+    streamed like the reference streams it (src/dap_to_bed.py:14-18), never held as a whole.
+    dap.txt is parsed on the device (the host only moves bytes; MEMO_TEXT_PARSE=host selects the
+    pyarrow parser); the .lengths files are parsed on the host."""
     from . import io
     if args.lengths_paths is not None:
         return 0, io.iter_lengths_columns(args.lengths_paths)
-    it = io.iter_dap_text(args.dap_path)
+    if os.environ.get("MEMO_TEXT_PARSE", "device") == "host":
+        it = io.iter_dap_text(args.dap_path, byte_range=byte_range)
+    else:
+        it = io.iter_dap_text_device(args.dap_path, byte_range=byte_range,
+                                     block_bytes=int(os.environ.get("MEMO_TEXT_BLOCK_BYTES", 128 << 20)))
     first = next(it, None)
     if first is None:
         return 0, iter(())
@@ -187,18 +193,11 @@ def main_rank(args, records):
     dist.init_process_group("nccl", device_id=dev)
     try:
         lo, hi, prev = io.split_text_rows(args.dap_path, world, rank)
-        it = io.iter_dap_text(args.dap_path, byte_range=(lo, hi))
-        first = next(it, None)
+        pos0, blocks = dap_blocks(args, byte_range=(lo, hi))
         part = f"{args.out_path}.part{rank:03d}"
-        stats = {}
         with open(part, "wb") as fh:
-            if first is not None:
-                def blocks():
-                    yield first[1]
-                    for _, block in it:
-                        yield block
-                halo = None if prev is None else np.array([int(x) for x in prev.split(b" ")][1:], dtype=np.int32)
-                stats = _stream(args, records, fh, first[0], blocks(), first_halo=halo, final=(rank == world - 1))
+            halo = None if prev is None else np.array([int(x) for x in prev.split(b" ")][1:], dtype=np.int32)
+            stats = _stream(args, records, fh, pos0, blocks, first_halo=halo, final=(rank == world - 1))
         # input that is not matching statistics needs the carry of everything before a shard:
         # one rank redoes the whole file with the exact streaming build
         flag = torch.tensor([1 if stats.get("general") else 0], dtype=torch.int32, device=dev)

@@ -163,6 +163,8 @@ class IndexStream:
         for _, length in self.records:
             self.starts.add(acc)
             acc += length
+        self.on_dev = False                 # the current chunk is being filled device to device (feed_device)
+        self.prev_last_row_dev = None       # last row of the previous chunk, on the device
         self.src = None                     # rows of the current chunk taken in place (pinned caller memory)
         self.last_row = None                # last row fed so far
         # last row of the chunk submitted before the current one
@@ -197,10 +199,37 @@ class IndexStream:
             ev.synchronize()
         return slot
 
+    def feed_device(self, block: torch.Tensor) -> None:
+        """Rows [pos, pos + n) of the DAP already on the device (int32 [n, C], e.g. from the
+        device text parser): copied into the chunk buffers on the stream's CUDA stream; the block
+        may be overwritten as soon as this returns (stream order)."""
+        if block.dim() != 2 or block.shape[1] != self.C or block.dtype != torch.int32 or not block.is_cuda:
+            raise MemoError(f"device DAP block must be int32 [n, {self.C}] on the GPU")
+        done = 0
+        while done < block.shape[0]:
+            if self.fill == self.chunk_rows:
+                self._submit(last=False)
+            slot = self._slot(self.k)
+            if self.fill == 0:
+                pos0 = self.pos
+                if self.segs_all is not None:
+                    slot["base"] = 1 if pos0 > self.pos_stream0 else 0
+                else:
+                    slot["base"] = 1 if (pos0 > self.pos_stream0 or self.first_halo) and pos0 not in self.starts else 0
+                self.on_dev = True
+            n = min(block.shape[0] - done, self.chunk_rows - self.fill)
+            b = slot["base"] + self.fill
+            slot["dev"][b:b + n].copy_(block[done:done + n], non_blocking=True)
+            self.fill += n
+            self.pos += n
+            done += n
+
     def feed(self, block) -> None:
         """Rows [pos, pos + n) of the DAP.  A pinned torch tensor is copied to the device straight
-        from where it is (it has to stay alive until finish()); anything else goes through the
-        stream's pinned staging."""
+        from where it is (it has to stay alive until finish()); a CUDA tensor is taken on the
+        device (feed_device); anything else goes through the stream's pinned staging."""
+        if isinstance(block, torch.Tensor) and block.is_cuda:
+            return self.feed_device(block)
         direct = isinstance(block, torch.Tensor) and block.is_pinned() and block.is_contiguous()
         if isinstance(block, torch.Tensor) and not direct:
             block = block.numpy()
@@ -267,23 +296,35 @@ class IndexStream:
             # the halo row = the record's previous row
             halo = (pos0 > self.pos_stream0 or self.first_halo) and pos0 not in self.starts
             segs = self._segments(pos0, n, halo, last)
-        src = self.src if self.src is not None else slot["pin"][:n]
-        self.src = None
-        if halo:
-            slot["pin_halo"].numpy()[0] = self.prev_last_row
         slot.update(n=n, pos0=pos0, halo=halo, last=last, segs=segs)
-        with torch.cuda.stream(self.copy_stream):
-            # (the build that read this slot's device buffer last is RING chunks back: collected)
-            # device chunk = [halo row,] rows: always starts at the (16-byte aligned) buffer base
+        if self.on_dev:
+            # rows were copied device to device as they arrived (feed_device); the halo row too
+            assert slot["base"] == (1 if halo else 0)
             if halo:
-                slot["dev"][0:1].copy_(slot["pin_halo"], non_blocking=True)
-            base = 1 if halo else 0
-            slot["dev"][base:base + n].copy_(src, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        slot["h2d"] = ev
-        self.main.wait_event(ev)
-        self.prev_last_row = self.last_row                 # next chunk's halo = this chunk's last row
+                prev = self.prev_last_row_dev
+                if prev is None:                           # (the shard's first halo row came from the host)
+                    prev = torch.from_numpy(self.prev_last_row.reshape(1, -1)).to(self.dev)
+                slot["dev"][0:1].copy_(prev, non_blocking=True)
+            # next chunk's halo = this chunk's last row
+            self.prev_last_row_dev = slot["dev"][slot["base"] + n - 1:slot["base"] + n].clone()
+            self.on_dev = False
+        else:
+            src = self.src if self.src is not None else slot["pin"][:n]
+            self.src = None
+            if halo:
+                slot["pin_halo"].numpy()[0] = self.prev_last_row
+            with torch.cuda.stream(self.copy_stream):
+                # (the build that read this slot's device buffer last is RING chunks back: collected)
+                # device chunk = [halo row,] rows: always starts at the (16-byte aligned) buffer base
+                if halo:
+                    slot["dev"][0:1].copy_(slot["pin_halo"], non_blocking=True)
+                base = 1 if halo else 0
+                slot["dev"][base:base + n].copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            slot["h2d"] = ev
+            self.main.wait_event(ev)
+            self.prev_last_row = self.last_row             # next chunk's halo = this chunk's last row
         if not self.general and segs:
             self._launch_fast(slot)
         slot["general"] = self.general

@@ -159,6 +159,69 @@ def iter_dap_text(path, block_bytes: int = 64 << 20, byte_range=None):
         raise ValueError(f"invalid literal for int() in dap.txt: {e}") from None
 
 
+def iter_dap_text_device(path, device=None, block_bytes: int = 128 << 20, byte_range=None):
+    """dap.txt parsed ON THE DEVICE: the file is read in blocks of whole lines into pinned
+    memory, the bytes go to the GPU and memo_dap_text_parse turns them into int32 rows (the
+    host never looks at a digit).  Yields (first position, device int32 [n, C]); a block is a
+    view of the parser's buffer, valid until the next one is requested.  byte_range = (lo, hi):
+    a rank's share of the file (split_text_rows)."""
+    import torch
+    from . import api
+    lo, hi = byte_range if byte_range is not None else (0, _os.path.getsize(path))
+    if hi <= lo:
+        return
+    with open(path, "rb") as fh:
+        fh.seek(lo)
+        first = fh.readline()
+        n_fields = len(first.split(b" ")) if first.strip() else 0
+        if n_fields == 0:
+            return
+        if n_fields < 2:
+            raise MemoError("dap.txt needs a position column and at least one genome column")
+        block_bytes = max(int(block_bytes), 4 * len(first) + 64)
+        parser = api.DapTextParser(n_fields - 1, block_bytes, device)
+        pin = torch.empty(block_bytes + 64, dtype=torch.uint8, pin_memory=True)
+        view = pin.numpy()
+        fh.seek(lo)
+        left, carry = hi - lo, 0                       # bytes of the share not read yet; bytes carried over
+        while left > 0 or carry > 0:
+            want = min(left, block_bytes - carry)
+            got = fh.readinto(memoryview(view)[carry:carry + want]) if want > 0 else 0
+            left -= got
+            n = carry + got
+            if got == 0 and left > 0:
+                left = 0                               # (file shorter than expected)
+            if left == 0:
+                if n and view[n - 1] != 10:            # last line of the share without its newline
+                    view[n] = 10
+                    n += 1
+                cut = n
+            else:
+                # the block ends with its last whole line; the rest opens the next block
+                tail = view[max(0, n - (1 << 16)):n]
+                nl = np.flatnonzero(tail == 10)
+                if nl.size == 0:
+                    nl = np.flatnonzero(view[:n] == 10)
+                    if nl.size == 0:
+                        raise MemoError("dap.txt: a line longer than the text block")
+                    cut = int(nl[-1]) + 1
+                else:
+                    cut = max(0, n - (1 << 16)) + int(nl[-1]) + 1
+            if cut == 0:
+                break
+            head = bytes(view[:min(cut, 24)])
+            try:
+                pos_first = int(head.split(b" ", 1)[0])
+            except ValueError:
+                raise ValueError("invalid literal for int() in dap.txt") from None
+            rows = parser.parse(pin, cut, pos_first)      # (synchronises: the pinned block is free again)
+            if rows.shape[0]:
+                yield pos_first, rows
+            carry = n - cut
+            if carry:
+                view[:carry] = view[cut:n].copy()
+
+
 def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 20, read_bytes: int = 4 << 20):
     """Per-genome MONI `*.lengths` / `*.lengths.vert` files streamed side by side: yields int32
     [n, C] blocks of consecutive pivot positions (all files advance together; memory use is

@@ -488,6 +488,53 @@ def test_index_stream_memory_is_bounded_by_the_chunk():
     assert np.array_equal(got[1][m], want_head[1][want_head[1] < 199_000])
 
 
+def test_dap_text_parsed_on_the_device(tmp_path):
+    """memo_dap_text_parse (dap.txt -> int32 rows on the GPU) against numpy: blocks cut at line
+    ends, a last line without newline, byte shares of a file, and everything int() would reject."""
+    from memo_b200 import io
+    from memo_b200._lib import MemoError
+    rng = np.random.default_rng(12)
+    L, C = 30_011, 7
+    vals = rng.integers(0, 3_000_000, (L, C))
+    vals[rng.random((L, C)) < 0.3] = rng.integers(0, 10, int((rng.random((L, C)) < 0.3).sum() * 0 + 1))[0]
+    vals[5, 2] = 2**31 - 1
+    text = "".join(f"{i + 40} " + " ".join(map(str, row)) + "\n" for i, row in enumerate(vals))
+    path = tmp_path / "dap.txt"
+    path.write_text(text)
+
+    def collect(p, **kw):
+        parts = [(p0, b.cpu().numpy()) for p0, b in io.iter_dap_text_device(str(p), **kw)]
+        return parts
+
+    for block in (1 << 12, 77_777, 1 << 26):
+        parts = collect(path, block_bytes=block)
+        assert parts[0][0] == 40 and np.array_equal(np.concatenate([b for _, b in parts]), vals), block
+        pos = 40
+        for p0, b in parts:
+            assert p0 == pos
+            pos += len(b)
+    nonl = tmp_path / "nonl.txt"
+    nonl.write_text(text[:-1])
+    assert np.array_equal(np.concatenate([b for _, b in collect(nonl, block_bytes=50_000)]), vals)
+    rows, expect = [], 40
+    for r in range(3):
+        lo, hi, prev = io.split_text_rows(str(path), 3, r)
+        for p0, b in collect(path, block_bytes=20_000, byte_range=(lo, hi)):
+            assert p0 == expect
+            expect += len(b)
+            rows.append(b)
+    assert np.array_equal(np.concatenate(rows), vals)
+    bad = tmp_path / "bad.txt"
+    for body, exc in (("0 1 2\n1 3 x\n", ValueError), ("0 1 2\n1  3\n", ValueError), ("0 1 2\n\n1 3 4\n", ValueError),
+                      ("0 1 2\n1 3\n", MemoError), ("0 1 2\n1 3 4 5\n", MemoError), ("0 1 2\n2 3 4\n", MemoError),
+                      ("0 1 2\n1 3 2147483648\n", MemoError), ("0 1 -2\n", ValueError)):
+        bad.write_text(body)
+        with pytest.raises(exc):
+            collect(bad)
+    bad.write_text("")
+    assert collect(bad) == []
+
+
 def test_view_bins_match_oracle(tmp_path):
     """`memo view` binning kernel (plot_conservation.py:46-58) against the oracle, through the
     API and through the drop-in's preprocess_data; uint8 and uint16 vectors, bins that do not
