@@ -108,9 +108,6 @@ class IndexRows:
     replays: int
     general: bool              # produced by the three-pass general build
 
-    def end_u32(self) -> torch.Tensor:
-        return self.end
-
     def to_host(self):
         """(rec_idx, start, end, order) int64 numpy arrays."""
         n = self.n

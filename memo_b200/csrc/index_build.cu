@@ -35,6 +35,7 @@
 // result[MEMO_RES_IRREGULAR].
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "index_fast.cuh"
@@ -309,7 +310,6 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     const long long queue_bytes = plan->narrow ? 4 * 40 * (long long)((2 * C + 2) | 1) : 0;   // NARROW_QCAP entries
     const long long budget = (220 * 1024 / plan->warps - 1024 - queue_bytes - 2 * (MAX_TILE_ROWS + 4)) / plan->stages;
     long long T;
-    size_t extra = 0;
     if (plan->narrow) {
         // tiles: whole warp steps of 32 * rpl rows, ~4.5-9 KB of DAP per tile
         const long long step = 32ll * plan->rpl;
@@ -323,7 +323,6 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         if (G < 1) G = 1;
         plan->R = (int)G;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
-        extra = 0;
     } else {
         // strips of R rows stream through the ring in chunks of T rows: as many as keep four
         // CTAs of `warps` warps on an SM (~9 KB per warp)
@@ -348,7 +347,6 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_descs = (uint32_t)o;   o += sizeof(TileDesc) * MAX_STAGES;
     plan->off_stg = (uint32_t)o;     o += (size_t)queue_bytes;
     plan->off_list = (uint32_t)o;    o += plan->narrow ? 2 * (size_t)(T + 4) : 0;
-    (void)extra;
     plan->warp_smem = (uint32_t)align_up(o, 128);
     plan->smem = (size_t)plan->warp_smem * plan->warps;
     MEMO_REQUIRE(plan->smem <= 227 * 1024, "tile configuration needs %zu B of shared memory", plan->smem);
@@ -397,6 +395,34 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
     plan->total = off;
     return MEMO_OK;
+}
+
+// Resident CTAs per SM of a streaming kernel for a block size and dynamic shared-memory size on
+// the current device.  The kernel's shared-memory limit is raised to the device maximum once per
+// (device, kernel) and never lowered; the occupancy query runs once per shape (it used to run,
+// with the attribute call, on every launch: 362 chunks for chr1 x 94 at 256 MB).
+int stream_ctas_per_sm(stream_kernel_t kern, int threads, size_t smem) {
+    struct Entry { int dev; stream_kernel_t k; int threads; size_t smem; int n; };
+    static std::mutex mu;
+    static Entry cache[64];
+    static int n_cache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    bool raised = false;
+    for (int i = 0; i < n_cache; ++i) {
+        if (cache[i].dev != dev || cache[i].k != kern) continue;
+        raised = true;
+        if (cache[i].threads == threads && cache[i].smem == smem) return cache[i].n;
+    }
+    if (!raised &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess) n = 0;
+    if (n_cache == 64) n_cache = 0;
+    cache[n_cache++] = Entry{dev, kern, threads, smem, n};
+    return n;
 }
 
 // which build a shape takes: 0 = lane-per-row tiles (narrow rows), 2 = the strip kernel with
@@ -492,17 +518,16 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         return launch_wide2(dap, rows, n_cols, ld, segs, n_seg, opts, out_start, out_end, out_order, out_cap,
                             seg_out_end, result, workspace, workspace_bytes, stream);
     FastPlan plan;
-    long long* tstart = new long long[(size_t)n_seg + 1];
+    std::vector<long long> tstart_v((size_t)n_seg + 1);
+    long long* tstart = tstart_v.data();
     int rc = make_fast_plan(rows, n_cols, ld, out_cap, segs, n_seg, opts, &plan, tstart);
-    if (rc != MEMO_OK) { delete[] tstart; return rc; }
+    if (rc != MEMO_OK) return rc;
     if (workspace_bytes < plan.total || workspace == nullptr) {
-        delete[] tstart;
         set_error("workspace too small: %zu < %zu", workspace_bytes, plan.total);
         return MEMO_ERR_WORKSPACE;
     }
-    cudaError_t e0 = cudaMemsetAsync(result, 0, sizeof(int64_t) * MEMO_RES_SLOTS, stream);
-    if (e0 != cudaSuccess) { delete[] tstart; set_error("memset result: %s", cudaGetErrorString(e0)); return MEMO_ERR_CUDA; }
-    if (n_seg == 0 || plan.n_units == 0) { delete[] tstart; return MEMO_OK; }
+    MEMO_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(int64_t) * MEMO_RES_SLOTS, stream));
+    if (n_seg == 0 || plan.n_units == 0) return MEMO_OK;
 
     char* ws = static_cast<char*>(workspace);
     // pageable host -> device copies are staged by the runtime before returning,
@@ -511,7 +536,6 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
                                      cudaMemcpyHostToDevice, stream);
     cudaError_t e2 = cudaMemcpyAsync(ws + plan.off_tstart, tstart, sizeof(long long) * (size_t)(n_seg + 1),
                                      cudaMemcpyHostToDevice, stream);
-    delete[] tstart;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         set_error("segment table upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         return MEMO_ERR_CUDA;
@@ -550,9 +574,8 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         return MEMO_ERR_UNSUPPORTED;
     }
     const int threads = plan.warps * 32;
-    MEMO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    int per_sm = 0;
-    MEMO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, plan.smem));
+    const int per_sm_q = stream_ctas_per_sm(kern, threads, plan.smem);
+    int per_sm = per_sm_q;
     if (per_sm < 1) {
         set_error("stream kernel does not fit on an SM (smem %zu B)", plan.smem);
         return MEMO_ERR_UNSUPPORTED;

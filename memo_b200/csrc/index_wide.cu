@@ -33,8 +33,11 @@
 namespace memo {
 namespace {
 
+#ifndef MEMO_WIDE_MIN_CTAS
+#define MEMO_WIDE_MIN_CTAS 1
+#endif
 template <int KPL, bool ORDER>
-__global__ void __launch_bounds__(256) wide_kernel(const FastParams P) {
+__global__ void __launch_bounds__(256, MEMO_WIDE_MIN_CTAS) wide_kernel(const FastParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
