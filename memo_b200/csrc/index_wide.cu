@@ -33,11 +33,17 @@
 namespace memo {
 namespace {
 
-#ifndef MEMO_WIDE_MIN_CTAS
-#define MEMO_WIDE_MIN_CTAS 1
+// (experiment knob: -DMEMO_WIDE_MIN_CTAS=4 caps the kernel at 64 registers for 32 resident warps;
+//  measured slower, DESIGN.md 4.3b.  Without it ptxas settles on 80 registers = 4 CTAs of 6 warps;
+//  note that __launch_bounds__(256, 1) is NOT the same as __launch_bounds__(256): it lets ptxas
+//  take 105 registers and halves the occupancy)
+#ifdef MEMO_WIDE_MIN_CTAS
+#define MEMO_WIDE_BOUNDS __launch_bounds__(256, MEMO_WIDE_MIN_CTAS)
+#else
+#define MEMO_WIDE_BOUNDS __launch_bounds__(256)
 #endif
 template <int KPL, bool ORDER>
-__global__ void __launch_bounds__(256, MEMO_WIDE_MIN_CTAS) wide_kernel(const FastParams P) {
+__global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

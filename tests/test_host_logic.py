@@ -312,3 +312,28 @@ def test_parquet_compress_bed_empty_bed_raises_like_the_reference(tmp_path):
     bed.write_text("")
     with pytest.raises(Exception):
         parquet_compress_bed.bed_to_parquet(str(bed), str(tmp_path / "e.parquet"))
+
+
+def test_stream_kernels_keep_their_register_budget():
+    """Occupancy is part of the design: four CTAs of six warps of the strip
+    kernel per SM need <= 85 registers per thread (ptxas settles on 80; `__launch_bounds__(256, 1)`
+    instead of `__launch_bounds__(256)` once let it take 105 and halved the occupancy)."""
+    import shutil
+    from memo_b200 import _build
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    _build.build()
+    out = subprocess.run([exe, "-res-usage", os.path.join(_build.CSRC, "index_wide.o")], capture_output=True,
+                         text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    wide = {k: v for k, v in regs.items() if "wide_kernelILi3E" in k}
+    assert len(wide) == 2 and all(v <= 85 for v in wide.values()), wide
