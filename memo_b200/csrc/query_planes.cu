@@ -123,6 +123,15 @@ template <int B, int GS, bool MEMB>
 __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const PlaneParams P) {
     constexpr int GB = GS == 8 ? 3 : 2;              // digits fixed by the position inside a group
     __shared__ __align__(16) uint32_t smem[QP_WARPS][MEMB ? QP_WORDS_M + 32 : QP_WORDS];
+    // conservation read-out: byte v of a digit plane -> the 8 result bytes it contributes to
+    // (bit i of v in byte i), looked up instead of spread by multiplies
+    __shared__ uint2 spread_lut[MEMB ? 1 : 256];
+    if (!MEMB) {
+        for (int v = threadIdx.x; v < 256; v += QP_WARPS * 32)
+            spread_lut[v] = make_uint2((((uint32_t)v & 0xFu) * 0x00204081u) & 0x01010101u,
+                                       (((uint32_t)v >> 4) * 0x00204081u) & 0x01010101u);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     uint32_t* const planes = smem[threadIdx.x >> 5];
     const int WPT = P.WPT, n_docs = P.n_docs;
@@ -306,14 +315,16 @@ __global__ void __launch_bounds__(QP_WARPS * 32) query_planes_kernel(const Plane
             // digit planes -> bytes: output word j holds positions 4j .. 4j+3
             uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t acc = 0u;
+            for (int j = 0; j < 4; ++j) {                  // byte j of every digit plane: positions 8j .. 8j+7
+                uint32_t lo = 0u, hi = 0u;
 #pragma unroll
                 for (int bb = 0; bb < B; ++bb) {
-                    const uint32_t nib = (dg[bb] >> (4 * j)) & 0xFu;
-                    acc += ((nib * 0x00204081u) & 0x01010101u) << bb;
+                    const uint2 sp = spread_lut[(dg[bb] >> (8 * j)) & 0xFFu];
+                    lo += sp.x << bb;                       // (digits do not overlap: add = or)
+                    hi += sp.y << bb;
                 }
-                w[j] = acc;
+                w[2 * j] = lo;
+                w[2 * j + 1] = hi;
             }
             uint8_t* const o = out_k + t0 + 32 * wc;
             if (32 * wc + 32 <= tn) {
