@@ -51,6 +51,33 @@ struct Profile {
 thread_local Profile g_profile;
 int pick_build(int32_t C, int32_t ld, const memo_index_opts_t* opts);
 
+// ---------------------------------------------------------------- prep
+// The record runs and their first units go to the device as KERNEL PARAMETERS, and the same
+// launch clears the result slots and the control words: a build then contains no copy-engine
+// operation at all.  (cudaMemcpyAsync from pageable memory synchronises the stream before it
+// copies -- with a 256 MB chunk copy queued ahead of the build, the streaming host path stalled
+// for that copy on every chunk -- and small copies / memsets may queue behind a large host ->
+// device copy on the same engine.)
+constexpr int PREP_SEGS = 64;
+struct PrepArgs {
+    memo_segment_t segs[PREP_SEGS];
+    long long tstart[PREP_SEGS + 1];
+    memo_segment_t* d_segs;
+    long long* d_tstart;
+    int64_t* result;            // MEMO_RES_SLOTS slots, cleared by the first batch
+    unsigned int* ctrl;         // 64 control words, cleared by the first batch
+    int first, n;               // runs [first, first + n) and tstart[first .. first + n]
+};
+__global__ void prep_kernel(const PrepArgs a) {
+    const int t = threadIdx.x;
+    if (t < a.n) a.d_segs[a.first + t] = a.segs[t];
+    if (t <= a.n) a.d_tstart[a.first + t] = a.tstart[t];
+    if (a.first == 0) {
+        if (t < MEMO_RES_SLOTS) a.result[t] = 0;
+        if (t < 64) a.ctrl[t] = 0u;
+    }
+}
+
 // ---------------------------------------------------------------- scan
 // partial[b] = index rows of tile block b; the last block to arrive turns
 // partial[] into exclusive block offsets and writes the grand total.
@@ -164,6 +191,7 @@ __device__ __forceinline__ uint32_t gather_block_scan(
 // block chain.
 __global__ void __launch_bounds__(SCAN_THREADS)
 strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long long* __restrict__ tile_off,
+                  const uint32_t* __restrict__ unit_pos0, const uint32_t* __restrict__ unit_aux,
                   const uint32_t* __restrict__ first_cnt, const int32_t* __restrict__ unit_next,
                   const BlockRec* __restrict__ pool, uint32_t pool_cap, long long n_tiles,
                   const unsigned long long* __restrict__ block_base,
@@ -209,7 +237,8 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
         }
         for (uint32_t b0 = c0; b0 < c1; b0 += 32 * U) {
             unsigned long long src[U];
-            uint32_t v[U][3];
+            uint32_t base_pos[U], chr_start[U];
+            uint2 v[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const uint32_t d = b0 + j * 32 + lane;
@@ -229,23 +258,24 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
                         cnt = rec.cnt;
                         nx = rec.next;
                     }
-                    if (ok && off + r < (unsigned long long)scr_cap) src[j] = off + r;
+                    if (ok && off + r < (unsigned long long)scr_cap) {
+                        src[j] = off + r;
+                        base_pos[j] = unit_pos0[blk_lo + u];      // (the lanes of a warp share a few units)
+                        chr_start[j] = unit_aux[blk_lo + u];
+                    }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < U; ++j) {
-                if (src[j] != ~0ull) {
-                    const uint32_t* row = scr + src[j] * 3;
-                    v[j][0] = row[0]; v[j][1] = row[1]; v[j][2] = row[2];
-                }
-            }
+            for (int j = 0; j < U; ++j)
+                if (src[j] != ~0ull) v[j] = reinterpret_cast<const uint2*>(scr)[src[j]];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const unsigned long long d = base + b0 + j * 32 + lane;
                 if (src[j] != ~0ull && d < (unsigned long long)out_cap) {
-                    out_start[d] = (int32_t)v[j][0];
-                    out_end[d] = v[j][1];
-                    out_order[d] = (int32_t)v[j][2];
+                    const uint32_t rowf = v[j].y >> 16;
+                    out_start[d] = (int32_t)(rowf == SCR_ROW_CHR ? chr_start[j] : base_pos[j] + rowf);
+                    out_end[d] = v[j].x;
+                    out_order[d] = (int32_t)(v[j].y & 0xFFFFu);
                 }
             }
         }
@@ -264,8 +294,14 @@ struct FastPlan {
     long long n_units, n_blocks;
     size_t smem;
     size_t off_segs, off_tstart, off_cnt, off_off, off_partial, off_ctrl, off_fcnt, off_next, off_pool,
-        off_scratch, total;
+        off_pos0, off_aux, off_scratch, total;
 };
+
+// tuning knobs read once from the environment (experiments; the defaults are the measured best)
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const memo_segment_t* segs,
                    int32_t n_seg, const memo_index_opts_t* opts, FastPlan* plan, long long* tstart_host) {
@@ -321,6 +357,8 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         // strips of R tiles (~1 K rows): one scratch block chain and one gather unit each
         long long G = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records : (1024 + T - 1) / T;
         if (G < 1) G = 1;
+        MEMO_REQUIRE(G * T <= SCR_MAX_UNIT_ROWS, "strip of %lld x %lld rows: at most %lld rows per unit", G, T,
+                     SCR_MAX_UNIT_ROWS);
         plan->R = (int)G;
         plan->stage_bytes = (uint32_t)align_up((size_t)((T + 2) * row_bytes + 16), 128);
     } else {
@@ -333,10 +371,14 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         if (T > MAX_TILE_ROWS) T = MAX_TILE_ROWS;
         if (T * row_bytes + 160 + 128 * plan->kpl > budget) T = (budget - 160 - 128 * plan->kpl) / row_bytes;
         if (T < 1) T = 1;
-        // about 128 compare rows per strip, a whole number of chunks (predecessor row included)
+        // about 460 compare rows per strip, a whole number of chunks (predecessor row included): the
+        // sorted row is built from scratch once per strip (~300 warp instructions; at 128 rows
+        // per strip that was 2.6 per row, 4 % of the kernel)
+        static const long long strip_rows = env_int("MEMO_WIDE_STRIP_ROWS", 460);
         long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records
-                                                           : (128 / T > 1 ? 128 / T : 1) * T - 1;
+                                                           : (strip_rows / T > 1 ? strip_rows / T : 1) * T - 1;
         if (R < 1) R = 1;
+        MEMO_REQUIRE(R <= SCR_MAX_UNIT_ROWS, "strip of %lld rows: at most %lld rows per unit", R, SCR_MAX_UNIT_ROWS);
         plan->R = (int)R;
         // (slots of lanes past the last column read up to 128 * kpl bytes beyond a row)
         plan->stage_bytes = (uint32_t)align_up((size_t)(T * row_bytes + 32 + 128 * plan->kpl), 128);
@@ -392,7 +434,9 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
     plan->off_fcnt = off;    off = align_up(off + 4 * ns, 256);
     plan->off_next = off;    off = align_up(off + 4 * ns, 256);
     plan->off_pool = off;    off = align_up(off + sizeof(BlockRec) * (size_t)plan->pool_cap, 256);
-    plan->off_scratch = off; off = align_up(off + 12 * (size_t)plan->scr_cap + 48, 256);
+    plan->off_pos0 = off;    off = align_up(off + 4 * ns, 256);
+    plan->off_aux = off;     off = align_up(off + 4 * ns, 256);
+    plan->off_scratch = off; off = align_up(off + 4 * SCR_WORDS * (size_t)(plan->scr_cap + SCR_DUMP_ROWS) + 48, 256);
     plan->total = off;
     return MEMO_OK;
 }
@@ -526,19 +570,24 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         set_error("workspace too small: %zu < %zu", workspace_bytes, plan.total);
         return MEMO_ERR_WORKSPACE;
     }
-    MEMO_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(int64_t) * MEMO_RES_SLOTS, stream));
-    if (n_seg == 0 || plan.n_units == 0) return MEMO_OK;
+    if (n_seg == 0 || plan.n_units == 0) {
+        MEMO_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(int64_t) * MEMO_RES_SLOTS, stream));
+        return MEMO_OK;
+    }
 
     char* ws = static_cast<char*>(workspace);
-    // pageable host -> device copies are staged by the runtime before returning,
-    // so the host buffers may be released right after these calls
-    cudaError_t e1 = cudaMemcpyAsync(ws + plan.off_segs, segs, sizeof(memo_segment_t) * (size_t)n_seg,
-                                     cudaMemcpyHostToDevice, stream);
-    cudaError_t e2 = cudaMemcpyAsync(ws + plan.off_tstart, tstart, sizeof(long long) * (size_t)(n_seg + 1),
-                                     cudaMemcpyHostToDevice, stream);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        set_error("segment table upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-        return MEMO_ERR_CUDA;
+    for (int first = 0; first < n_seg; first += PREP_SEGS) {
+        PrepArgs a;
+        a.n = n_seg - first < PREP_SEGS ? n_seg - first : PREP_SEGS;
+        a.first = first;
+        for (int i = 0; i < a.n; ++i) a.segs[i] = segs[first + i];
+        for (int i = 0; i <= a.n; ++i) a.tstart[i] = tstart[first + i];
+        a.d_segs = reinterpret_cast<memo_segment_t*>(ws + plan.off_segs);
+        a.d_tstart = reinterpret_cast<long long*>(ws + plan.off_tstart);
+        a.result = result;
+        a.ctrl = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl);
+        prep_kernel<<<1, 96, 0, stream>>>(a);
+        MEMO_LAUNCH_CHECK(1);
     }
     const bool order = opts ? (opts->order_mode != 0) : true;
 
@@ -560,9 +609,13 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.strip_counter = reinterpret_cast<unsigned long long*>(ws + plan.off_ctrl + 128);
     P.pool_counter = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 192);
     P.first_cnt = reinterpret_cast<uint32_t*>(ws + plan.off_fcnt);
+    P.unit_pos0 = reinterpret_cast<uint32_t*>(ws + plan.off_pos0);
+    P.unit_aux = reinterpret_cast<uint32_t*>(ws + plan.off_aux);
     P.unit_next = reinterpret_cast<int32_t*>(ws + plan.off_next);
     P.pool = reinterpret_cast<BlockRec*>(ws + plan.off_pool);
     P.pool_cap = plan.pool_cap;
+    static const int prefetch = env_int("MEMO_WIDE_PREFETCH", 1);
+    P.prefetch = prefetch;
     unsigned int* done = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 64);
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(ws + plan.off_partial);
     P.result = result;
@@ -585,7 +638,6 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     const long long need = (plan.n_units + plan.warps - 1) / plan.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    MEMO_CUDA_TRY(cudaMemsetAsync(ws + plan.off_ctrl, 0, 256, stream));
     profile_begin(stream);
     kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     MEMO_LAUNCH_CHECK(1);
@@ -600,7 +652,8 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
         if (split < 1) split = 1;
         if (split > 32) split = 32;
         strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
-            P.tile_cnt, P.tile_off, P.first_cnt, P.unit_next, P.pool, P.pool_cap, plan.n_units, partial,
+            P.tile_cnt, P.tile_off, P.unit_pos0, P.unit_aux, P.first_cnt, P.unit_next, P.pool, P.pool_cap,
+            plan.n_units, partial,
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
             seg_out_end);
     }

@@ -12,8 +12,12 @@ constexpr int MAX_TILE_ROWS = 960;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // tiles per scan / gather block
+constexpr int SCR_WORDS = 2;                            // words per scratch row
+constexpr uint32_t SCR_ROW_CHR = 0xFFFFu;               // row field of a chr-end row
+constexpr long long SCR_MAX_UNIT_ROWS = 65000;          // DAP rows per unit: the row field has 16 bits
+constexpr long long SCR_DUMP_ROWS = 4096;              // rows behind the scratch area that take the stores of chunks past its end
 
-struct TileDesc {
+struct alignas(16) TileDesc {
     int n;              // rows in the stage (narrow: T compare rows after row 0)
     int off;            // wide: word offset of row 0 inside the stage data; narrow: strip
     uint32_t pos_h;     // record-relative position of row 0
@@ -51,13 +55,17 @@ struct FastParams {
     uint32_t stage_bytes;
     uint32_t warp_smem;                // shared-memory bytes per warp
     uint32_t off_bars, off_descs, off_stg, off_list;   // inside the warp's region
-    uint32_t* scr;                     // scratch index rows (unordered blocks): {start, end, order} x scr_cap
+    uint32_t* scr;                     // scratch index rows (unordered blocks): {end, row << 16 | order} x scr_cap
+                                       // (row = BED start - the unit's unit_pos0, SCR_ROW_CHR = a chr-end row:
+                                       //  BED start = the unit's unit_aux)
     long long out_cap;                 // 0 = count only
     long long scr_cap;                 // rows of the scratch area
     uint32_t chunk;                    // scratch rows a warp reserves per atomicAdd
     uint32_t* tile_cnt;                // [n_tiles] index rows of the unit
     unsigned long long* tile_off;      // [n_tiles] scratch row of the unit's (first) block
     // wide: a strip whose output crosses scratch chunks continues in further blocks
+    uint32_t* unit_pos0;               // [n_tiles] position the unit's row numbers count from
+    uint32_t* unit_aux;                // [n_tiles] BED start of the unit's chr-end rows (the record length)
     uint32_t* first_cnt;               // [n_tiles] rows of the first block
     int32_t* unit_next;                // [n_tiles] next block (index into pool) or -1
     BlockRec* pool;                    // [pool_cap] further blocks
@@ -65,6 +73,7 @@ struct FastParams {
     unsigned int* pool_counter;
     unsigned long long* cursor;        // scratch allocation cursor
     unsigned long long* strip_counter; // wide: next strip to hand out
+    int32_t prefetch;                  // wide: prefetch a strip's next chunk into L2
     int64_t* result;
 };
 
@@ -104,7 +113,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_addr(bar))
         : "memory");
 }
+// the same range on its way into L2 only (no shared-memory destination, no completion)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
+
+// one scratch row: MEM end + (row << 16 | order), row = BED start - the unit's pos0 or SCR_ROW_CHR
+__device__ __forceinline__ void scr_store(uint32_t* dst, uint32_t end, uint32_t row, uint32_t order) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(end, (row << 16) | order);
+}
 
 // Output of one work unit (strip) of a warp.  A warp reserves P.chunk rows of the
 // scratch area with one atomicAdd and appends the index rows of its strips to
@@ -119,10 +137,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 struct StripOut {
     uint32_t* w_ptr = nullptr;                     // next scratch row of the warp's chunk
     uint32_t w_left = 0;                           // rows left in the chunk
-    bool w_ok = true;                              // the chunk lies inside the scratch area
     unsigned long long w_end = 0;                  // scratch row index after the chunk
     unsigned long long blk_off = 0;                // open block of the strip
-    uint32_t blk_cnt = 0, total = 0;               // rows in the open block / in the strip
+    uint32_t blk_left0 = 0;                        // w_left when the open block began
+    uint32_t total = 0;                            // rows of the strip's closed blocks
     int nblk = 0, last_rec = -1;                   // blocks closed so far; pool index of the last one
     long long strip = 0;
 
@@ -130,10 +148,12 @@ struct StripOut {
         strip = strip_id;
         nblk = 0;
         blk_off = w_end - w_left;
-        blk_cnt = 0;
+        blk_left0 = w_left;
         total = 0;
     }
     __device__ __forceinline__ void close_block(const FastParams& P, int lane) {
+        const uint32_t blk_cnt = blk_left0 - w_left;
+        total += blk_cnt;
         if (nblk == 0) {
             if (lane == 0) {
                 P.tile_off[strip] = blk_off;
@@ -162,27 +182,31 @@ struct StripOut {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(P.cursor, want);
         base = __shfl_sync(FULL, base, 0);
-        w_ptr = P.scr + base * 3;
         w_left = (uint32_t)want;
         w_end = base + want;
-        w_ok = w_end <= (unsigned long long)P.scr_cap;    // (a chunk past the end stores nothing:
-        blk_off = base;                                   //  its rows are counted, the caller retries)
-        blk_cnt = 0;
+        // a chunk past the end of the scratch area writes to the dump rows behind it (its rows are
+        // counted, the gather skips them, the caller retries with a larger out_cap)
+        w_ptr = P.scr + (w_end <= (unsigned long long)P.scr_cap ? base : (unsigned long long)P.scr_cap) * SCR_WORDS;
+        blk_off = base;
+        blk_left0 = w_left;
     }
-    // `n` consecutive scratch rows ({start, end, order} records) for the strip's next index
-    // rows; returns the first, or nullptr if the scratch area is exhausted
+    // `n` consecutive scratch rows (8-byte records, scr_record) for the strip's next index
+    // rows (n <= SCR_DUMP_ROWS); returns the first.  Always writable: see new_chunk.
     __device__ __forceinline__ uint32_t* reserve(const FastParams& P, uint32_t n, int lane) {
         if (n > w_left) new_chunk(P, n, lane);
         uint32_t* const at = w_ptr;
-        w_ptr += 3 * n;
+        w_ptr += SCR_WORDS * n;
         w_left -= n;
-        blk_cnt += n;
-        total += n;
-        return w_ok ? at : nullptr;
+        return at;
     }
-    __device__ __forceinline__ void end(const FastParams& P, int lane) {
+    // pos0: the position the strip's row numbers count from; aux: BED start of its chr-end rows
+    __device__ __forceinline__ void end(const FastParams& P, int lane, uint32_t pos0, uint32_t aux) {
         close_block(P, lane);
-        if (lane == 0) P.tile_cnt[strip] = total;
+        if (lane == 0) {
+            P.tile_cnt[strip] = total;
+            P.unit_pos0[strip] = pos0;
+            P.unit_aux[strip] = aux;
+        }
     }
 };
 

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
     int s = 0;
     uint32_t parity = 0;
     StripOut so;                                      // the strip's output blocks
+    uint32_t strip_pos0 = 0;                          // position of row 0 of the strip's first tile
     // queue of flagged rows (ring): entry = {start, limit, e[CT], f[CT]}, odd stride
     constexpr int ESTR = (2 * CT + 2) | 1;
     constexpr int QCAP = NARROW_QCAP;
@@ -228,14 +229,14 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         if (total) {
             uint32_t* dst = so.reserve(P, total, lane);
             unsigned mm = dst ? m : 0u;
-            dst += (incl - cnt) * 3u;
+            dst += (incl - cnt) * SCR_WORDS;
+            // (all queued rows belong to the open strip: the queue is emptied when a strip ends)
+            const uint32_t rowf = lim != 0xFFFFFFFFu ? SCR_ROW_CHR : p - strip_pos0;
             while (mm) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
-                dst[0] = p;
-                dst[1] = q[2 + c];
-                dst[2] = (uint32_t)(c + 1);
-                dst += 3;
+                scr_store(dst, q[2 + c], rowf, (uint32_t)(c + 1));
+                dst += SCR_WORDS;
             }
         }
         __syncwarp();
@@ -248,7 +249,10 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         mbar_wait(&bars[s], parity);
         const TileDesc d = descs[s];
         if (d.flags & WD_END) break;
-        if (d.flags & WD_FIRST) so.begin(d.off);
+        if (d.flags & WD_FIRST) {
+            so.begin(d.off);
+            strip_pos0 = d.pos_h;
+        }
         const uint32_t* const sdata = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes);
 
         // ---------------- phase A: ordered list of the live rows that moved a MEM end
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(256) narrow_kernel(const FastParams P) {
         if (d.flags & WD_LAST) {
             while (qn > 0) flush(qn < 32 ? qn : 32);
         }
-        if (d.flags & WD_LAST) so.end(P, lane);
+        if (d.flags & WD_LAST) so.end(P, lane, strip_pos0, d.rec_len);
         __syncwarp();                    // stage s and the list are free again
         if (lane == 0) issue(s);
         if (++s == S) {

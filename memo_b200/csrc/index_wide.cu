@@ -48,7 +48,8 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
-    const int C = P.C, ld = P.ld, S = P.stages, T = P.T, R = P.R;
+    const int C = P.C, S = P.stages, T = P.T, R = P.R;
+    const int ld_param = P.ld;
 
     unsigned char* const wbase = smem_raw + (size_t)warp * P.warp_smem;
     uint64_t* const bars = (uint64_t*)(wbase + P.off_bars);
@@ -60,77 +61,99 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
     seg.row_begin = seg.n_rows = 0;
     seg.pos0 = seg.rec_len = seg.rec_id = seg.flags = 0;
     unsigned long long look = 0;          // next strip (fetched one strip ahead: hides the atomic)
-    long long p_strip = 0, p_row = 0, p_left = 0;
-    uint32_t p_pos = 0;
+    unsigned long long p_addr = 0;        // byte offset of the strip's next row in the DAP
+    uint32_t p_left = 0, p_pos = 0;       // rows of the strip still to fetch; position of the next one
+    int p_strip = 0;
     bool p_first = false, p_done = false, p_lastseg = false;
+    const uint32_t ldb = (uint32_t)ld_param * 4u, Cb = (uint32_t)C * 4u;
+    const unsigned long long lim = (unsigned long long)P.total_bytes & ~15ull;
+    const unsigned char* const src = reinterpret_cast<const unsigned char*>(P.dap);
     if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
 
+    // (per chunk: 32-bit arithmetic on top of the strip's running byte offset)
     auto issue = [&](int s) {
         if (p_done) return;
         uint64_t* bar = &bars[s];
-        TileDesc d;
-        d.pad = 0; d.r_hi = 0;
         if (p_left == 0) {
-            p_strip = (long long)look;
-            if (p_strip >= P.n_tiles) {
-                d.n = 0; d.off = 0; d.pos_h = 0; d.rec_len = 0; d.flags = WD_END; d.r_lo = 0;
+            const long long strip = (long long)look;
+            if (strip >= P.n_tiles) {
+                TileDesc d;
+                d.n = 0; d.off = 0; d.pos_h = 0; d.rec_len = 0; d.flags = WD_END; d.r_lo = 0; d.r_hi = 0; d.pad = 0;
                 descs[s] = d;
                 mbar_arrive(bar);
                 p_done = true;
                 return;
             }
             look = atomicAdd(P.strip_counter, 1ull);
-            if (p_strip < c_lo || p_strip >= c_hi) {
+            if (strip < c_lo || strip >= c_hi) {
                 int s_lo = 0, s_hi = P.n_seg - 1;
                 while (s_lo < s_hi) {
                     const int mid = (s_lo + s_hi + 1) >> 1;
-                    if (P.seg_tile_start[mid] <= p_strip) s_lo = mid; else s_hi = mid - 1;
+                    if (P.seg_tile_start[mid] <= strip) s_lo = mid; else s_hi = mid - 1;
                 }
                 c_lo = P.seg_tile_start[s_lo];
                 c_hi = P.seg_tile_start[s_lo + 1];
                 seg = P.segs[s_lo];
             }
-            const long long t = p_strip - c_lo;
+            const long long t = strip - c_lo;
             const int primed = (seg.flags & MEMO_SEG_PRIMED) ? 1 : 0;
             const long long m = seg.n_rows - primed;                     // compare rows of the run
             long long n_cmp = m - t * R;
             if (n_cmp > R) n_cmp = R;
             if (n_cmp < 0) n_cmp = 0;
-            p_row = seg.row_begin + primed + t * R - 1;                  // the strip's predecessor row
-            p_left = n_cmp + 1;
-            p_pos = (uint32_t)seg.pos0 + (uint32_t)(p_row - seg.row_begin);
+            const long long row = seg.row_begin + primed + t * R - 1;    // the strip's predecessor row
+            p_addr = (unsigned long long)row * ldb;
+            p_left = (uint32_t)n_cmp + 1u;
+            p_pos = (uint32_t)seg.pos0 + (uint32_t)(row - seg.row_begin);
             p_first = true;
-            p_lastseg = (p_strip + 1 == c_hi) && (seg.flags & MEMO_SEG_CHR_END);
+            p_lastseg = (strip + 1 == c_hi) && (seg.flags & MEMO_SEG_CHR_END);
+            p_strip = (int)strip;
         }
-        const long long n = p_left < T ? p_left : T;
-        const long long start = p_row * (long long)ld * 4;
-        const long long end = (p_row + n - 1) * (long long)ld * 4 + (long long)C * 4;
-        const long long a0 = start & ~15ll;
-        long long a1 = (end + 15) & ~15ll;
-        const long long lim = P.total_bytes & ~15ll;
-        if (a1 > lim) a1 = lim;
+        const uint32_t n = p_left < (uint32_t)T ? p_left : (uint32_t)T;
+        const uint32_t head = (uint32_t)p_addr & 15u;               // the copy starts at a 16-byte boundary
+        const uint32_t bytes = (n - 1u) * ldb + Cb;                 // first row's first byte .. last row's last column
+        uint32_t len = (head + bytes + 15u) & ~15u;
+        const unsigned long long a0 = p_addr - head;
+        const bool last = n == p_left;
+        TileDesc d;
         d.n = (int)n;
-        d.off = (int)((start - a0) >> 2);
+        d.off = (int)(head >> 2);
         d.pos_h = p_pos;
         d.rec_len = (uint32_t)seg.rec_len;
-        d.flags = (p_first ? WD_FIRST : 0) | (n == p_left ? WD_LAST : 0) | ((n == p_left && p_lastseg) ? WD_CHR : 0);
-        d.r_lo = (int)p_strip;
+        d.flags = (p_first ? WD_FIRST : 0) | (last ? WD_LAST : 0) | ((last && p_lastseg) ? WD_CHR : 0);
+        d.r_lo = p_strip;
+        d.r_hi = 0;
+        d.pad = ld_param;                // the row stride: read back per chunk, it then lives in a register
+                                         // instead of being reloaded from the parameter bank per row
         descs[s] = d;
         unsigned char* data = wbase + (size_t)s * P.stage_bytes;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.dap);
-        // the last < 16 bytes of the buffer cannot be part of a 16-byte granular bulk copy
-        for (long long b = (a1 > a0 ? a1 : a0); b < end; b += 4)
-            *reinterpret_cast<uint32_t*>(data + (b - a0)) = *reinterpret_cast<const uint32_t*>(src + b);
-        if (a1 > a0) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));
-            bulk_g2s(data, src + a0, (uint32_t)(a1 - a0), bar);
+        if (a0 + len > lim) {
+            // the last < 16 bytes of the buffer cannot be part of a 16-byte granular bulk copy
+            const unsigned long long end = p_addr + bytes;
+            const unsigned long long a1 = lim > a0 ? lim : a0;
+            for (unsigned long long b = a1; b < end; b += 4)
+                *reinterpret_cast<uint32_t*>(data + (b - a0)) = *reinterpret_cast<const uint32_t*>(src + b);
+            len = (uint32_t)(a1 - a0);
+        }
+        if (len) {
+            mbar_arrive_expect_tx(bar, len);
+            bulk_g2s(data, src + a0, len, bar);
         } else {
             mbar_arrive(bar);
         }
-        p_row += n;
-        p_pos += (uint32_t)n;
+        p_addr += (unsigned long long)n * ldb;
+        p_pos += n;
         p_left -= n;
         p_first = false;
+        // the strip's next chunk on its way into L2 while this one is worked on: its copy, issued when
+        // this stage is free again, then finds the rows in L2 (one stage per warp: the wait for a
+        // chunk is the latency of its copy)
+        if (P.prefetch && p_left > 0) {
+            const uint32_t nn = p_left < (uint32_t)T ? p_left : (uint32_t)T;
+            const uint32_t h2 = (uint32_t)p_addr & 15u;
+            const uint32_t l2 = (h2 + nn * ldb + 15u) & ~15u;
+            if (p_addr - h2 + l2 <= lim) bulk_prefetch_l2(src + (p_addr - h2), l2);
+        }
     };
 
     if (lane == 0) {
@@ -159,11 +182,13 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
 #pragma unroll
     for (int k = 0; k < KPL; ++k) prv[k] = A[k] = 0;
     StripOut so;                       // the strip's output blocks
+    uint32_t strip_pos0 = 0;           // position of the strip's predecessor row: scratch rows count from it
     uint32_t irr_acc = 0;
 
-    // index rows of one row: em[k] / endv[k] per slot, `p` = BED start.  Output
+    // index rows of one row: em[k] / endv[k] per slot, `row` = BED start - strip_pos0 (or
+    // SCR_ROW_CHR: chr-end rows).  Output
     // order: ORDER -> position ibase + k; else column lane + 32 k.
-    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t p) {
+    auto emit = [&](const bool (&em)[KPL], const uint32_t (&endv)[KPL], uint32_t row) {
         unsigned b[KPL];
         uint32_t total = 0, rank = 0;
 #pragma unroll
@@ -172,159 +197,203 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
             total += __popc(b[k]);
         }
         if (total == 0) return;
-        uint32_t* const dst0 = so.reserve(P, total, lane);             // warp uniform
-        if (dst0 != nullptr) {
-            if (ORDER) {
+        uint32_t* const dst0 = so.reserve(P, total, lane);             // warp uniform, always writable
+        if (ORDER) {
 #pragma unroll
-                for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
-            }
+            for (int k = 0; k < KPL; ++k) rank += __popc(b[k] & ltmask);
+        }
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
+            if (em[k])
+                scr_store(dst0 + rk * SCR_WORDS, endv[k], row, (uint32_t)(ORDER ? ibase + k : lane + 32 * k) + 1u);
+            if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
+        }
+    };
+
+    // a row in which some cell moved: `prev` / `cur` = raw values of the row before / the row,
+    // dk = cur + 1 - prev (last slot masked), `pos` = the row's position
+    auto changed = [&](const uint32_t (&prev)[KPL], const uint32_t (&cur)[KPL], const uint32_t (&dk)[KPL],
+                       uint32_t pos) {
+        bool em[KPL];
+        uint32_t endv[KPL];
+        if (ORDER) {
+            // cells whose MEM end moved up (a decrease makes the input irregular:
+            // flagged through irr_acc, skipped here)
+            bool ch[KPL];
+            uint32_t cnt = 0;
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
-                const uint32_t rk = ORDER ? rank : rank + __popc(b[k] & ltmask);
-                if (em[k]) {
-                    uint32_t* dst = dst0 + rk * 3u;
-                    dst[0] = p;
-                    dst[1] = endv[k];
-                    dst[2] = (uint32_t)(ORDER ? ibase + k : lane + 32 * k) + 1u;
+                ch[k] = (int)dk[k] > 0;
+                cnt += ch[k] ? 1u : 0u;
+            }
+            const uint32_t nchg = __reduce_add_sync(FULL, cnt);
+            if (nchg == 1) {
+                // the common case, one cell x -> y: the positions holding x <= A <= y
+                // shift down by one, y lands on the first of them, and exactly those
+                // positions can emit.  (Positions past the last column hold 0 and never
+                // emit: a compare row has pos >= 1.)  Every other lane contributes 0 to the
+                // two maxima.
+                uint32_t myx = 0, myy = 0;
+#pragma unroll
+                for (int k = 0; k < KPL; ++k)
+                    if (ch[k]) { myx = prev[k]; myy = cur[k]; }
+                const uint32_t x = __reduce_max_sync(FULL, myx) + (pos - 1u);
+                const uint32_t y = __reduce_max_sync(FULL, myy) + pos;
+                uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                if (lane == 0) up = 0xFFFFFFFFu;
+                // in place, last slot first: slot kk needs the old value of slot kk - 1
+#pragma unroll
+                for (int kk = KPL - 1; kk >= 0; --kk) {
+                    const uint32_t before = kk == 0 ? up : A[kk - 1];
+                    const uint32_t old = A[kk];
+                    const bool inr = old >= x && old <= y;
+                    const uint32_t nw = inr ? min(before, y) : old;
+                    em[kk] = nw != old && old >= pos;
+                    endv[kk] = old;
+                    A[kk] = nw;
                 }
-                if (ORDER) rank += em[k] ? 1u : 0u; else rank += __popc(b[k]);
+            } else {
+                uint32_t Aold[KPL];
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) Aold[k] = A[k];
+                // one cell per lane and round
+                unsigned todo = 0;
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) todo |= (ch[k] ? 1u : 0u) << k;
+                unsigned m;
+                while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
+                    uint32_t myx = 0, myd = 0;
+#pragma unroll
+                    for (int k = KPL - 1; k >= 0; --k)
+                        if (todo & (1u << k)) { myx = prev[k]; myd = dk[k]; }
+                    todo &= todo - 1;
+                    do {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        // delete x, insert y > x
+                        const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
+                        const uint32_t y = x + __shfl_sync(FULL, myd, src);
+                        uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
+                        if (lane == 0) up = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int kk = KPL - 1; kk >= 0; --kk) {
+                            const uint32_t before = kk == 0 ? up : A[kk - 1];
+                            A[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
+                        }
+                    } while (m);
+                }
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) {
+                    em[k] = A[k] != Aold[k] && Aold[k] >= pos;
+                    endv[k] = Aold[k];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const uint32_t e = prev[k] + (pos - 1u);
+                em[k] = (int)dk[k] > 0 && e >= pos;
+                endv[k] = e;
             }
         }
+        emit(em, endv, pos - strip_pos0);
     };
 
     int s = 0;
     uint32_t parity = 0;
     for (;;) {
         mbar_wait(&bars[s], parity);
-        const TileDesc d = descs[s];
+        TileDesc d = descs[s];
+        // (warp reductions: the compiler then knows that flags and row count are warp uniform and
+        //  emits no divergence guards around the votes of the row loop)
+        d.flags = (int)__reduce_or_sync(FULL, (unsigned)d.flags);
+        d.n = (int)__reduce_max_sync(FULL, (unsigned)d.n);
         if (d.flags & WD_END) break;
+        const int ld = d.pad;
         // the lane's column of the stage: row r, slot k at lp[r * ld + 32 * k]
         const uint32_t* lp = reinterpret_cast<const uint32_t*>(wbase + (size_t)s * P.stage_bytes) + d.off + lane;
-        uint32_t pos = d.pos_h;                                  // position of the row at lp
-        int left = d.n;
+        uint32_t pos_end = d.pos_h + (uint32_t)d.n;              // position after the chunk's last row
+        int left = d.n;                                          // rows from lp on
         if (d.flags & WD_FIRST) {
             // strip start: row 0 only primes the state
 #pragma unroll
             for (int k = 0; k < KPL; ++k) prv[k] = lp[32 * k];
             if (ORDER) {
 #pragma unroll
-                for (int k = 0; k < KPL; ++k) A[k] = cvalid[k] ? prv[k] + pos : 0u;
+                for (int k = 0; k < KPL; ++k) A[k] = cvalid[k] ? prv[k] + d.pos_h : 0u;
                 group_sort_desc<32, KPL>(A, lane);
             }
             so.begin(d.r_lo);
+            strip_pos0 = d.pos_h;
             lp += ld;
-            ++pos;
             --left;
         }
-        // one row: `cur` = its raw values (returned), `prev` = the row before
-        auto row = [&](const uint32_t (&prev)[KPL], uint32_t (&cur)[KPL]) {
-            uint32_t dk[KPL], acc = 0;
+        // The chunk's rows.  Most rows move nothing: the inner loop only loads a row, compares it with
+        // the one before and votes; it touches neither the sorted row nor the output state, alternates
+        // between two register sets (no copies) and hands on nothing but the place of a row that moved
+        // something (lp, left): that row and the one before it are then read again from the stage
+        // (the row before the chunk's first row lives in registers only: `carry`).
+        const int left_first = left;
+        uint32_t carry[KPL];
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) carry[k] = prv[k];
+        for (;;) {
+            {
+                uint32_t ra[KPL], rb[KPL];
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) ra[k] = prv[k];
+                // a row against the one before: true if some cell moved (warp vote)
+                auto moved = [&](const uint32_t* rowp, const uint32_t (&before)[KPL], uint32_t (&row)[KPL]) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) row[k] = rowp[32 * k];
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) {
+                        const uint32_t dd = row[k] + 1u - before[k];
+                        acc |= (k == KPL - 1) ? (dd & vm[k]) : dd;
+                    }
+                    return __any_sync(FULL, acc != 0u) != 0;
+                };
+                // (leaves the loop with left > 0 and lp at a row that moved something, or left == 0)
+                while (left >= 2) {
+                    if (moved(lp, ra, rb)) break;
+                    if (moved(lp + ld, rb, ra)) {
+                        lp += ld;
+                        --left;
+                        break;
+                    }
+                    lp += 2 * ld;
+                    left -= 2;
+                }
+                // (after a hit on the second row of a pair with one row left, `ra` is the hit row itself:
+                //  the vote below then sees row + 1 - row = 1 and leaves the hit alone)
+                if (left == 1 && !moved(lp, ra, rb)) {
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) ra[k] = rb[k];
+                    lp += ld;
+                    left = 0;
+                }
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) prv[k] = ra[k];          // (only read when the chunk is done)
+            }
+            if (left == 0) break;
+            uint32_t pv[KPL], cu[KPL], dk[KPL], acc = 0;
+            const bool first = left == left_first;                // warp uniform
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
-                cur[k] = lp[32 * k];
-                dk[k] = cur[k] + 1u - prev[k];
-                acc |= k == KPL - 1 ? (dk[k] & vm[k]) : dk[k];
+                cu[k] = lp[32 * k];
+                pv[k] = first ? carry[k] : (lp - ld)[32 * k];
+                dk[k] = cu[k] + 1u - pv[k];
+                if (k == KPL - 1) dk[k] &= vm[k];
+                acc |= dk[k];
             }
-            if (__any_sync(FULL, acc != 0u)) {
-                irr_acc |= acc;
-                bool em[KPL];
-                uint32_t endv[KPL];
-                if (ORDER) {
-                    // cells whose MEM end moved up (a decrease makes the input irregular:
-                    // flagged through irr_acc, skipped here)
-                    bool ch[KPL];
-                    uint32_t cnt = 0;
+            irr_acc |= acc;
+            changed(pv, cu, dk, pos_end - (uint32_t)left);
 #pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        ch[k] = (int)(k == KPL - 1 ? (dk[k] & vm[k]) : dk[k]) > 0;
-                        cnt += ch[k] ? 1u : 0u;
-                    }
-                    const unsigned ball = __ballot_sync(FULL, cnt != 0u);
-                    const uint32_t nchg = __reduce_add_sync(FULL, cnt);
-                    if (nchg == 1) {
-                        // the common case, one cell x -> y: the positions holding x <= A <= y
-                        // shift down by one, y lands on the first of them, and exactly those
-                        // positions can emit
-                        uint32_t myx = prev[0], myd = dk[0];
-#pragma unroll
-                        for (int k = 1; k < KPL; ++k)
-                            if (ch[k]) { myx = prev[k]; myd = dk[k]; }
-                        const int src = __ffs(ball) - 1;
-                        const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
-                        const uint32_t y = x + __shfl_sync(FULL, myd, src);
-                        uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
-                        if (lane == 0) up = 0xFFFFFFFFu;
-                        // in place, last slot first: slot kk needs the old value of slot kk - 1
-#pragma unroll
-                        for (int kk = KPL - 1; kk >= 0; --kk) {
-                            const uint32_t before = kk == 0 ? up : A[kk - 1];
-                            const uint32_t old = A[kk];
-                            const bool inr = old >= x && old <= y;
-                            const uint32_t nw = inr ? min(before, y) : old;
-                            em[kk] = nw > old && old >= pos && ibase + kk < C;
-                            endv[kk] = old;
-                            A[kk] = nw;
-                        }
-                    } else {
-                        uint32_t Aold[KPL];
-#pragma unroll
-                        for (int k = 0; k < KPL; ++k) Aold[k] = A[k];
-                        // one cell per lane and round
-                        unsigned todo = 0;
-#pragma unroll
-                        for (int k = 0; k < KPL; ++k) todo |= (ch[k] ? 1u : 0u) << k;
-                        unsigned m;
-                        while ((m = __ballot_sync(FULL, todo != 0u)) != 0u) {
-                            uint32_t myx = 0, myd = 0;
-#pragma unroll
-                            for (int k = KPL - 1; k >= 0; --k)
-                                if (todo & (1u << k)) { myx = prev[k]; myd = dk[k]; }
-                            todo &= todo - 1;
-                            do {
-                                const int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                // delete x, insert y > x
-                                const uint32_t x = __shfl_sync(FULL, myx, src) + (pos - 1u);
-                                const uint32_t y = x + __shfl_sync(FULL, myd, src);
-                                uint32_t up = __shfl_up_sync(FULL, A[KPL - 1], 1);
-                                if (lane == 0) up = 0xFFFFFFFFu;
-#pragma unroll
-                                for (int kk = KPL - 1; kk >= 0; --kk) {
-                                    const uint32_t before = kk == 0 ? up : A[kk - 1];
-                                    A[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
-                                }
-                            } while (m);
-                        }
-#pragma unroll
-                        for (int k = 0; k < KPL; ++k) {
-                            em[k] = A[k] > Aold[k] && Aold[k] >= pos && ibase + k < C;
-                            endv[k] = Aold[k];
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KPL; ++k) {
-                        const uint32_t e = prev[k] + (pos - 1u);
-                        em[k] = (int)(dk[k] & vm[k]) > 0 && e >= pos;
-                        endv[k] = e;
-                    }
-                }
-                emit(em, endv, pos);
-            }
+            for (int k = 0; k < KPL; ++k) prv[k] = cu[k];
             lp += ld;
-            ++pos;
-        };
-        // rows alternate between two register sets (no copies); prv is the set that
-        // holds the last row seen when a chunk ends
-        uint32_t alt[KPL];
-        for (; left >= 2; left -= 2) {
-            row(prv, alt);
-            row(alt, prv);
-        }
-        if (left) {
-            row(prv, alt);
-#pragma unroll
-            for (int k = 0; k < KPL; ++k) prv[k] = alt[k];
+            --left;
         }
         if (d.flags & WD_LAST) {
             if (d.flags & WD_CHR) {                 // chr-end rows after the run's last row
@@ -332,14 +401,14 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
                 uint32_t endv[KPL];
 #pragma unroll
                 for (int k = 0; k < KPL; ++k) {
-                    const uint32_t e = ORDER ? A[k] : prv[k] + (pos - 1u);
+                    const uint32_t e = ORDER ? A[k] : prv[k] + (pos_end - 1u);
                     const bool valid = ORDER ? (ibase + k < C) : cvalid[k];
                     em[k] = valid && e >= d.rec_len;
                     endv[k] = min(e, 2u * d.rec_len);
                 }
-                emit(em, endv, d.rec_len);
+                emit(em, endv, SCR_ROW_CHR);
             }
-            so.end(P, lane);
+            so.end(P, lane, strip_pos0, d.rec_len);
         }
         __syncwarp();                    // stage s is free again
         if (lane == 0) issue(s);
@@ -359,9 +428,13 @@ stream_kernel_t select_wide_kernel(int n_cols, bool order, int* kpl_out) {
     if (kpl_out) *kpl_out = kpl;
 #define MEMO_WIDE(KK) \
     if (kpl == KK) return order ? wide_kernel<KK, true> : wide_kernel<KK, false>;
+#ifdef MEMO_WIDE_ONLY            // (SASS experiments: one instantiation)
+    MEMO_WIDE(MEMO_WIDE_ONLY)
+#else
     MEMO_WIDE(1) MEMO_WIDE(2) MEMO_WIDE(3) MEMO_WIDE(4) MEMO_WIDE(5) MEMO_WIDE(6) MEMO_WIDE(7) MEMO_WIDE(8)
     MEMO_WIDE(9) MEMO_WIDE(10) MEMO_WIDE(11) MEMO_WIDE(12) MEMO_WIDE(13) MEMO_WIDE(14) MEMO_WIDE(15)
     MEMO_WIDE(16)
+#endif
 #undef MEMO_WIDE
     return nullptr;
 }

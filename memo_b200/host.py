@@ -344,7 +344,13 @@ class IndexStream:
         with torch.cuda.stream(self.back_stream):
             self.back_stream.wait_event(ev)
             slot["pin_res"].copy_(slot["res"], non_blocking=True)
-            slot["pin_soe"] = soe.to("cpu", non_blocking=True)
+            # (into PINNED memory: `.to("cpu", non_blocking=True)` lands in pageable memory, and a
+            #  device -> pageable copy returns only when it is done -- one host stall per chunk)
+            pin = slot.get("pin_soe_buf")
+            if pin is None or pin.numel() < soe.numel():
+                pin = slot["pin_soe_buf"] = torch.empty(max(64, soe.numel()), dtype=torch.int64, pin_memory=True)
+            slot["pin_soe"] = pin[:soe.numel()]
+            slot["pin_soe"].copy_(soe, non_blocking=True)
             if not self.on_device:
                 slot["pin_out"].copy_(slot["out"], non_blocking=True)
             done = torch.cuda.Event()
@@ -486,7 +492,10 @@ def build_index(dap_host, records: Optional[Sequence[Tuple[str, int]]], order: b
     def on_rows(rec_counts, dev_rows):
         n = dev_rows.shape[1]
         room(n)
-        state["blk"][:, state["n"]:state["n"] + n].copy_(dev_rows, non_blocking=True)
+        # (one contiguous copy per column: a strided [3, n] copy across devices goes through
+        #  temporaries in pageable memory and blocks the host)
+        for r in range(3):
+            state["blk"][r, state["n"]:state["n"] + n].copy_(dev_rows[r], non_blocking=True)
         state["n"] += n
         for rid, c in rec_counts:
             if state["rec_counts"] and state["rec_counts"][-1][0] == rid:
