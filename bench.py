@@ -581,7 +581,7 @@ def extra_config(name, rec_len, C, membership, seed, k, dev, steps, peak, peak_s
             "value": rec_len * steps / (t["total_ms"] * 1e-3), "unit": "bp/s",
             "ms_per_step": t["total_ms"] / steps, "index_ms": t["idx_ms"], "query_ms": t["qry_ms"],
             "index_rows": wl.n_all, "roofline": r["roofline"], "roofline_index_build": r["roofline_index_build"],
-            "roofline_query": r["roofline_query"],
+            "roofline_query": r["roofline_query"], "clocks": t["clocks"],
             "roofline_query_l2_flushed": {"query_ms": q_ms, "achieved": bytes_q / (q_ms * 1e-3) / 1e9,
                                           "frac": bytes_q / (q_ms * 1e-3) / 1e9 / peak,
                                           "note": "query timed alone, 512 MB written between launches"}}
