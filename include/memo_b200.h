@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 6
+#define MEMO_B200_ABI_VERSION 7
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -192,6 +192,17 @@ size_t memo_synth_workspace_bytes(int64_t rows, int32_t n_cols);
 int memo_synth_dap(int32_t* dap, int64_t row0, int64_t rows, int32_t n_cols, int32_t ld,
                    int64_t rec_len, uint64_t seed, int32_t dense,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* BED rows of the index as dap_to_bed.py prints them (src/dap_to_bed.py:100-109,
+ * print('\t'.join(map(str, [header, start, end, annot])))): "name TAB f1 TAB f2 TAB f3 LF" per
+ * row, for n rows of ONE record (f1 / f2 / f3 device arrays as memo_index_build writes them;
+ * `name`: host bytes, at most 256).  out_text (device) needs memo_format_bed_max_bytes(n,
+ * name_len) bytes; *out_len (device int64) receives the byte count. */
+size_t memo_format_bed_workspace_bytes(int64_t n);
+size_t memo_format_bed_max_bytes(int64_t n, int32_t name_len);
+int memo_format_bed(const int32_t* f1, const uint32_t* f2, const int32_t* f3, int64_t n, const char* name,
+                    int32_t name_len, char* out_text, int64_t* out_len, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Query result text, byte-identical to src/memo_query.py print_res :65-71.
  * conservation: vals device uint8/uint16 [n] -> "%d\n" per value into out_text

@@ -55,6 +55,9 @@ SIGNATURES = {
                                    _vp, _vp, _sz, _vp]),
     "memo_synth_workspace_bytes": (_sz, [_i64, _i32]),
     "memo_synth_dap": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _u64, _i32, _vp, _sz, _vp]),
+    "memo_format_bed_workspace_bytes": (_sz, [_i64]),
+    "memo_format_bed_max_bytes": (_sz, [_i64, _i32]),
+    "memo_format_bed": (C.c_int, [_vp, _vp, _vp, _i64, C.c_char_p, _i32, _vp, _vp, _vp, _sz, _vp]),
     "memo_format_workspace_bytes": (_sz, [_i64]),
     "memo_format_conservation": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "memo_format_membership": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),

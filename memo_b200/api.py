@@ -348,6 +348,47 @@ def format_conservation(vals: torch.Tensor) -> bytes:
     return text[:m].cpu().numpy().tobytes()
 
 
+class BedFormatter:
+    """Index rows on the device -> the BED text dap_to_bed.py prints (src/dap_to_bed.py:100-109),
+    formatted on the device and copied back as bytes.  Keeps its device / pinned buffers."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise MemoError("no CUDA device: memo_b200 has no CPU fallback")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.text = self.ws = self.pin = None
+        self.out_len = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.pin_len = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+
+    def format(self, rows: torch.Tensor, name: str):
+        """rows: device int32 [3, n] (start, end as uint32 bits, order) of ONE record ->
+        uint8 numpy view of the text (valid until the next call)."""
+        _require_cuda(rows, "rows")
+        if rows.dtype != torch.int32 or rows.dim() != 2 or rows.shape[0] != 3 or rows.stride(1) != 1:
+            raise MemoError("rows must be int32 [3, n] with contiguous columns")
+        n = rows.shape[1]
+        nm = name.encode("utf-8")
+        need_text = self.lib.memo_format_bed_max_bytes(n, len(nm))
+        if self.text is None or self.text.numel() < need_text:
+            self.text = torch.empty(max(need_text, 1 << 16), dtype=torch.uint8, device=self.dev)
+        need_ws = self.lib.memo_format_bed_workspace_bytes(n)
+        if self.ws is None or self.ws.numel() < need_ws:
+            self.ws = torch.empty(max(need_ws, 1 << 12), dtype=torch.uint8, device=self.dev)
+        rc = self.lib.memo_format_bed(rows[0].data_ptr(), rows[1].data_ptr(), rows[2].data_ptr(), n, nm, len(nm),
+                                      self.text.data_ptr(), self.out_len.data_ptr(), self.ws.data_ptr(),
+                                      self.ws.numel(), _stream_ptr(self.dev))
+        _lib.check(rc, "memo_format_bed")
+        self.pin_len.copy_(self.out_len, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        m = int(self.pin_len[0])
+        if self.pin is None or self.pin.numel() < m:
+            self.pin = torch.empty(max(m + m // 4, 1 << 16), dtype=torch.uint8, pin_memory=True)
+        self.pin[:m].copy_(self.text[:m], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.pin.numpy()[:m]
+
+
 def format_membership(bits: torch.Tensor, n_docs: int) -> bytes:
     """Device membership bitmaps -> the bytes np.savetxt writes (memo_query.py:68)."""
     lib = _lib.load()

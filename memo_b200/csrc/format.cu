@@ -1,4 +1,4 @@
-// Query result text formatters on device.
+// Text formatters on device: query results and the BED rows of the index.
 //
 // Replace the text emitters of the reference's src/memo_query.py print_res
 // :65-71: conservation = one decimal integer per line (print(*rec, sep='\n')),
@@ -113,10 +113,129 @@ __global__ void fmt_membership_kernel(const uint32_t* __restrict__ bits, long lo
     }
 }
 
+// ---------------------------------------------------------------- BED rows
+// One index row as the reference prints it (src/dap_to_bed.py:105,
+// print('\t'.join(map(str, [header, start, end, annot])))): name TAB start TAB end TAB order LF.
+// All rows of a call belong to one record (one name).
+__device__ __forceinline__ int dec_digits(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+         : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+__device__ __forceinline__ char* put_dec(char* dst, uint32_t v, char term) {
+    const int l = dec_digits(v);
+    for (int d = l - 1; d >= 0; --d) {
+        dst[d] = (char)('0' + v % 10u);
+        v /= 10u;
+    }
+    dst[l] = term;
+    return dst + l + 1;
+}
+
+constexpr int BV = 8;            // rows per thread
+constexpr int BB = FT * BV;      // rows per block
+
+__global__ void __launch_bounds__(FT) bed_len_kernel(const int32_t* __restrict__ f1, const uint32_t* __restrict__ f2,
+                                                     const int32_t* __restrict__ f3, long long n, int name_len,
+                                                     unsigned long long* __restrict__ blocksum) {
+    const long long base = (long long)blockIdx.x * BB + (long long)threadIdx.x * BV;
+    unsigned len = 0;
+    for (int i = 0; i < BV; ++i)
+        if (base + i < n)
+            len += (unsigned)(name_len + 4 + dec_digits((uint32_t)f1[base + i]) + dec_digits(f2[base + i]) +
+                              dec_digits((uint32_t)f3[base + i]));
+    __shared__ unsigned red[FT / 32];
+    for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(FULL, len, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = len;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < FT / 32; ++i) t += red[i];
+        blocksum[blockIdx.x] = t;
+    }
+}
+
+struct BedName { char c[256]; };
+
+__global__ void __launch_bounds__(FT) bed_write_kernel(const int32_t* __restrict__ f1, const uint32_t* __restrict__ f2,
+                                                       const int32_t* __restrict__ f3, long long n, int name_len,
+                                                       const BedName name,
+                                                       const unsigned long long* __restrict__ blockoff,
+                                                       char* __restrict__ out) {
+    const long long base = (long long)blockIdx.x * BB + (long long)threadIdx.x * BV;
+    uint32_t a[BV], b[BV], c[BV];
+    unsigned len = 0;
+    for (int i = 0; i < BV; ++i) {
+        const bool live = base + i < n;
+        a[i] = live ? (uint32_t)f1[base + i] : 0u;
+        b[i] = live ? f2[base + i] : 0u;
+        c[i] = live ? (uint32_t)f3[base + i] : 0u;
+        if (live) len += (unsigned)(name_len + 4 + dec_digits(a[i]) + dec_digits(b[i]) + dec_digits(c[i]));
+    }
+    unsigned incl = len;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(FULL, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    __shared__ unsigned wsum[FT / 32];
+    __shared__ char s_name[256];
+    if (threadIdx.x < name_len) s_name[threadIdx.x] = name.c[threadIdx.x];
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    char* dst = out + blockoff[blockIdx.x] + woff + incl - len;
+    for (int i = 0; i < BV; ++i) {
+        if (base + i >= n) break;
+        for (int j = 0; j < name_len; ++j) dst[j] = s_name[j];
+        dst[name_len] = '\t';
+        dst = put_dec(dst + name_len + 1, a[i], '\t');
+        dst = put_dec(dst, b[i], '\t');
+        dst = put_dec(dst, c[i], '\n');
+    }
+}
+
 }  // namespace
 }  // namespace memo
 
 extern "C" {
+
+size_t memo_format_bed_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return memo::align_up(sizeof(unsigned long long) * (size_t)((n + memo::BB - 1) / memo::BB + 1), 256);
+}
+
+size_t memo_format_bed_max_bytes(int64_t n, int32_t name_len) {
+    if (n < 0) n = 0;
+    return (size_t)n * (size_t)(name_len + 4 + 10 + 10 + 10);
+}
+
+int memo_format_bed(const int32_t* f1, const uint32_t* f2, const int32_t* f3, int64_t n, const char* name,
+                    int32_t name_len, char* out_text, int64_t* out_len, void* workspace, size_t workspace_bytes,
+                    void* stream_) {
+    using namespace memo;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MEMO_REQUIRE(n >= 0 && out_len != nullptr, "bad n/out_len");
+    MEMO_REQUIRE(name_len >= 0 && name_len <= 256 && (name_len == 0 || name != nullptr),
+                 "record name of %d bytes (at most 256 on the device formatter)", name_len);
+    if (n == 0) {
+        MEMO_CUDA_TRY(cudaMemsetAsync(out_len, 0, sizeof(int64_t), stream));
+        return MEMO_OK;
+    }
+    MEMO_REQUIRE(f1 && f2 && f3 && out_text, "NULL buffer");
+    const long long nb = (n + BB - 1) / BB;
+    if (workspace == nullptr || workspace_bytes < sizeof(unsigned long long) * (size_t)nb) {
+        set_error("workspace too small");
+        return MEMO_ERR_WORKSPACE;
+    }
+    BedName nm;
+    for (int i = 0; i < 256; ++i) nm.c[i] = i < name_len ? name[i] : 0;
+    unsigned long long* bs = static_cast<unsigned long long*>(workspace);
+    bed_len_kernel<<<(unsigned)nb, FT, 0, stream>>>(f1, f2, f3, n, name_len, bs);
+    fmt_scan_kernel<<<1, 1024, 0, stream>>>(bs, nb, reinterpret_cast<long long*>(out_len));
+    bed_write_kernel<<<(unsigned)nb, FT, 0, stream>>>(f1, f2, f3, n, name_len, nm, bs, out_text);
+    MEMO_LAUNCH_CHECK(3);
+    return MEMO_OK;
+}
 
 size_t memo_format_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;

@@ -99,16 +99,29 @@ def dap_blocks(args, byte_range=None):
 def _stream(args, records, sink, pos0, blocks, **kw):
     """DAP blocks -> BED rows on `sink`, chunk by chunk.  Returns the stream's stats."""
     import pyarrow as pa
-    from . import host, io
+    from . import api, host, io
+    to_parquet = isinstance(sink, io.IndexParquetWriter)
+    # BED text is formatted on the device (MEMO_BED_FORMAT=host: the Arrow CSV writer)
+    on_device = not to_parquet and os.environ.get("MEMO_BED_FORMAT", "device") != "host" and \
+        all(len(r[0].encode("utf-8")) <= 256 for r in records)
     names = pa.array([r[0] for r in records], type=pa.utf8())
+    fmt = api.BedFormatter() if on_device else None
 
-    def on_rows(rec_counts, start, end, order):          # rows of one chunk, in print order
+    def on_rows_device(rec_counts, dev_rows):            # rows of one chunk on the device, in print order
+        a = 0
+        for rid, cnt in rec_counts:
+            sink.write(memoryview(fmt.format(dev_rows[:, a:a + cnt], records[rid][0])))
+            a += cnt
+
+    def on_rows_host(rec_counts, start, end, order):     # rows of one chunk, in print order
         table = io.index_batch(names, rec_counts, start, end, order)
-        if isinstance(sink, io.IndexParquetWriter):
+        if to_parquet:
             sink.write(table)
         else:
             io.write_bed(table, sink)
 
+    on_rows = on_rows_device if on_device else on_rows_host
+    kw = dict(kw, on_device=on_device)
     chunk_bytes = int(os.environ.get("MEMO_CHUNK_BYTES", host.DEFAULT_CHUNK_BYTES))
     stats = {}
     host.build_index_streaming(blocks, records, args.sort_lcps, on_rows, pos_first=pos0,

@@ -431,16 +431,17 @@ class IndexStream:
 
 def build_index_streaming(blocks, records, order: bool, on_rows, n_cols: Optional[int] = None,
                           pos_first: int = 0, device=None, chunk_bytes: int = DEFAULT_CHUNK_BYTES,
-                          stats: Optional[dict] = None, first_halo=None, final: bool = True, **tuning) -> int:
+                          stats: Optional[dict] = None, first_halo=None, final: bool = True,
+                          on_device: bool = False, **tuning) -> int:
     """Index rows of a DAP that arrives as an iterator of int32 [n, C] blocks of consecutive rows
-    (first row = global position pos_first); on_rows as in IndexStream.  first_halo / final: the
+    (first row = global position pos_first); on_rows / on_device as in IndexStream.  first_halo / final: the
     stream is one position shard of a larger DAP (IndexStream).  Returns the row count."""
     stream = None
     for block in blocks:
         if stream is None:
             C = block.shape[1] if n_cols is None else n_cols
             stream = IndexStream(records, order, C, on_rows, device=device, chunk_bytes=chunk_bytes,
-                                 pos_first=pos_first, first_halo=first_halo, **tuning)
+                                 pos_first=pos_first, first_halo=first_halo, on_device=on_device, **tuning)
         stream.feed(block)
     if stream is None:
         return 0

@@ -619,3 +619,51 @@ def test_cli_round_trip_example(example_golden, tmp_path, capsysbinary):
             argv = ["-b", str(pq_path), "-r", q["region"], "-k", str(q["k"]), "-n", str(q["n"]), "-o", str(out)]
             memo_query.main(memo_query.parse_arguments(argv + (["-m"] if q["membership"] else [])))
             assert out.read_text() == q["out"], q
+
+
+def test_bed_formatter_matches_python_text():
+    """memo_format_bed against '\\t'.join(map(str, ...)) (src/dap_to_bed.py:105): every digit count
+    of start / end / order, end beyond int32, empty and long record names, ragged block tails."""
+    import torch
+    from memo_b200 import api
+    rng = np.random.default_rng(77)
+    fmt = api.BedFormatter()
+    for n, name in ((0, "chr1"), (1, ""), (7, "c"), (2049, "chr1"), (50_000, "HG002#1#JAHKSE010000012.1" * 8)):
+        mag = rng.integers(0, 10, n)
+        start = np.minimum((10.0 ** mag * rng.random(n)).astype(np.int64), 2**31 - 1)
+        end = np.minimum(start + (10.0 ** rng.integers(0, 11, n) * rng.random(n)).astype(np.int64), 2**32 - 1)
+        order = np.minimum((10.0 ** rng.integers(0, 4, n) * rng.random(n)).astype(np.int64) + 1, 512)
+        if n > 3:
+            start[:3] = (0, 2**31 - 1, 999_999_999)
+            end[:3] = (0, 2**32 - 1, 1_000_000_000)
+            order[:3] = (1, 512, 10)
+        rows = torch.from_numpy(np.stack([start.astype(np.int32), end.astype(np.uint32).view(np.int32),
+                                          order.astype(np.int32)])).cuda()
+        want = "".join("\t".join(map(str, [name, s, e, o])) + "\n" for s, e, o in zip(start, end, order))
+        assert bytes(fmt.format(rows, name)).decode("utf-8") == want
+
+
+def test_cli_bed_text_device_equals_host_formatter(tmp_path, monkeypatch):
+    """dap_to_bed writes the same bytes with the device BED formatter and with the Arrow CSV
+    writer (MEMO_BED_FORMAT=host), several records and chunks."""
+    from memo_b200 import dap_to_bed
+    rng = np.random.default_rng(5)
+    recs = [("chrA", 7000), ("chrB_random", 3000), ("c", 1)]
+    L, C = sum(n for _, n in recs), 5
+    vals = mo.synth_dap(7000, C, 3)
+    vals = np.concatenate([vals, mo.synth_dap(3000, C, 4), mo.synth_dap(1, C, 5)])
+    dap = tmp_path / "dap.txt"
+    dap.write_text("".join(" ".join(map(str, [i] + list(r))) + "\n" for i, r in enumerate(vals)))
+    fai = tmp_path / "x.fa.fai"
+    fai.write_text("".join(f"{h}\t{n}\t7\t{n}\t{n + 1}\n" for h, n in recs))
+    monkeypatch.setenv("MEMO_CHUNK_BYTES", str(40_000))          # many chunks
+    outs = {}
+    for mode in ("device", "host"):
+        monkeypatch.setenv("MEMO_BED_FORMAT", mode)
+        args = dap_to_bed.parse_arguments(["--mem", "--overlap", "--order", "--fai", str(fai), "--dap", str(dap)])
+        dap_to_bed.check_args(args)
+        with open(tmp_path / f"{mode}.bed", "wb") as fh:
+            dap_to_bed.main(args, sink=fh)
+        outs[mode] = (tmp_path / f"{mode}.bed").read_bytes()
+    assert outs["device"] == outs["host"] and len(outs["device"]) > 0
+    assert outs["device"].decode() == mo.format_bed(recs, *mo.index_build(vals, recs, True))

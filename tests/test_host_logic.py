@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in memo_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.memo_abi_version() == 6
+    assert lib.memo_abi_version() == 7
 
 
 def test_struct_layouts_match_header():
