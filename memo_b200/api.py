@@ -364,8 +364,10 @@ class BedFormatter:
     def format(self, rows: torch.Tensor, name: str):
         """rows: device int32 [3, n] (start, end as uint32 bits, order) of ONE record ->
         uint8 numpy view of the text (valid until the next call)."""
-        _require_cuda(rows, "rows")
-        if rows.dtype != torch.int32 or rows.dim() != 2 or rows.shape[0] != 3 or rows.stride(1) != 1:
+        if not rows.is_cuda:
+            raise MemoError("rows must be a CUDA tensor (no CPU fallback)")
+        if rows.dtype != torch.int32 or rows.dim() != 2 or rows.shape[0] != 3 or \
+                (rows.shape[1] > 1 and rows.stride(1) != 1):
             raise MemoError("rows must be int32 [3, n] with contiguous columns")
         n = rows.shape[1]
         nm = name.encode("utf-8")

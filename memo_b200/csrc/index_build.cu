@@ -198,18 +198,24 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
                   const long long* __restrict__ seg_tile_start, int n_seg,
                   const uint32_t* __restrict__ scr, int32_t* __restrict__ out_start,
                   uint32_t* __restrict__ out_end, int32_t* __restrict__ out_order, long long out_cap,
-                  long long scr_cap, int64_t* __restrict__ seg_out_end) {
+                  long long scr_cap, int64_t* __restrict__ seg_out_end, int n_blocks, int split) {
     __shared__ uint32_t excl[SCAN_BLOCK + 1];
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     __shared__ uint32_t s_fcnt[SCAN_BLOCK];
     __shared__ int32_t s_next[SCAN_BLOCK];
     __shared__ unsigned long long s_off[SCAN_BLOCK];
-    const long long blk_lo = (long long)blockIdx.x * SCAN_BLOCK;
+    // The grid is one wave of resident CTAs; a CTA walks work items (block of units, slice of the
+    // block's rows), neighbouring CTAs share a block.  (One CTA per item left the last wave of a
+    // grid of n_blocks x split CTAs partly empty: 1060 CTAs on 740 slots at chr1 x 94.)
+    for (long long item = blockIdx.x; item < (long long)n_blocks * split; item += gridDim.x) {
+    const int blk = (int)(item / split), slice = (int)(item % split);
+    __syncthreads();                                            // (shared arrays of the previous item)
+    const long long blk_lo = (long long)blk * SCAN_BLOCK;
     const long long blk_hi = min(blk_lo + (long long)SCAN_BLOCK, n_tiles);
-    const unsigned long long base = block_base[blockIdx.x];
+    const unsigned long long base = block_base[blk];
     const uint32_t block_total = gather_block_scan(tile_cnt, n_tiles, blk_lo, blk_hi, base, seg_tile_start,
-                                                   n_seg, seg_out_end, blockIdx.y == 0, excl, wsum);
-    if (out_cap == 0 || block_total == 0) return;
+                                                   n_seg, seg_out_end, slice == 0, excl, wsum);
+    if (out_cap == 0 || block_total == 0) continue;
     const int n_units = (int)(blk_hi - blk_lo);
     for (int u = threadIdx.x; u < n_units; u += SCAN_THREADS) {
         s_off[u] = tile_off[blk_lo + u];
@@ -218,9 +224,9 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
     }
     if (threadIdx.x == 0) excl[n_units] = block_total;          // upper end of the last unit
     __syncthreads();
-    // this CTA's slice of the block's rows, in chunks of CH consecutive rows per warp
-    const uint32_t lo = (uint32_t)((unsigned long long)block_total * blockIdx.y / gridDim.y);
-    const uint32_t hi = (uint32_t)((unsigned long long)block_total * (blockIdx.y + 1) / gridDim.y);
+    // this item's slice of the block's rows, in chunks of CH consecutive rows per warp
+    const uint32_t lo = (uint32_t)((unsigned long long)block_total * slice / split);
+    const uint32_t hi = (uint32_t)((unsigned long long)block_total * (slice + 1) / split);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int U = 4;                            // rows per lane in flight
     constexpr uint32_t CH = 32 * U * 4;
@@ -279,6 +285,7 @@ strip_gather_kernel(const uint32_t* __restrict__ tile_cnt, const unsigned long l
                 }
             }
         }
+    }
     }
 }
 
@@ -465,11 +472,15 @@ int stream_ctas_per_sm(stream_kernel_t kern, int threads, size_t smem) {
         raised = true;
         if (cache[i].threads == threads && cache[i].smem == smem) return cache[i].n;
     }
-    if (!raised &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-        return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess) n = 0;
+    if (kern == nullptr) {                  // the gather kernel (static shared memory only)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, strip_gather_kernel, threads, smem) != cudaSuccess) n = 0;
+    } else {
+        if (!raised &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess) n = 0;
+    }
     if (n_cache == 64) n_cache = 0;
     cache[n_cache++] = Entry{dev, kern, threads, smem, n};
     return n;
@@ -652,16 +663,19 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
                                                                           done, result);
     MEMO_LAUNCH_CHECK(1);
     {
-        // every block of units is copied by `split` CTAs; all CTAs resident at once (8 x 256
-        // threads per SM): a few CTAs left over for a second wave would double the kernel's time
-        long long split = 8ll * device_sm_count() / plan.n_blocks;
+        // one wave of resident CTAs walks n_blocks x split work items (>= 6 items per CTA where the
+        // input is large enough: the slowest CTA then decides a few % of the kernel, not a wave)
+        const int occ = stream_ctas_per_sm(nullptr, SCAN_THREADS, 0);
+        const long long slots = (long long)(occ > 0 ? occ : 4) * device_sm_count();
+        long long split = (6 * slots + plan.n_blocks - 1) / plan.n_blocks;
         if (split < 1) split = 1;
         if (split > 32) split = 32;
-        strip_gather_kernel<<<dim3((unsigned)plan.n_blocks, (unsigned)split), SCAN_THREADS, 0, stream>>>(
+        long long grid = plan.n_blocks * split < slots ? plan.n_blocks * split : slots;
+        strip_gather_kernel<<<(unsigned)grid, SCAN_THREADS, 0, stream>>>(
             P.tile_cnt, P.tile_off, P.unit_pos0, P.unit_aux, P.first_cnt, P.unit_next, P.pool, P.pool_cap,
             plan.n_units, partial,
             P.seg_tile_start, n_seg, P.scr, out_start, out_end, out_order, out_cap, plan.scr_cap,
-            seg_out_end);
+            seg_out_end, (int)plan.n_blocks, (int)split);
     }
     MEMO_LAUNCH_CHECK(1);
     return MEMO_OK;
