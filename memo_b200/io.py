@@ -159,6 +159,47 @@ def iter_dap_text(path, block_bytes: int = 64 << 20, byte_range=None):
         raise ValueError(f"invalid literal for int() in dap.txt: {e}") from None
 
 
+_READ_POOL = None
+
+
+def _pread_into(fd: int, mv: memoryview, offset: int, piece: int = 8 << 20, threads: int = 0) -> int:
+    """Fill `mv` from file offset `offset`, optionally with several threads (os.preadv releases
+    the GIL; one thread copies out of the page cache at a few GB/s, which is most of the text
+    path's time).  threads = 0: MEMO_TEXT_READ_THREADS (default 4: 4.9 -> 8.9 GB/s of text on the B200 box).  Returns the number of bytes
+    read: less than len(mv) only at the end of the file."""
+    global _READ_POOL
+    n = len(mv)
+    if threads <= 0:
+        threads = int(_os.environ.get("MEMO_TEXT_READ_THREADS", "4"))
+    if n <= piece or threads <= 1:
+        got = 0
+        while got < n:
+            r = _os.preadv(fd, [mv[got:]], offset + got)
+            if r <= 0:
+                break
+            got += r
+        return got
+    if _READ_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _READ_POOL = ThreadPoolExecutor(threads)
+
+    def one(a):
+        b, got = min(n, a + piece), 0
+        while a + got < b:
+            r = _os.preadv(fd, [mv[a + got:b]], offset + a + got)
+            if r <= 0:
+                break
+            got += r
+        return got
+    counts = list(_READ_POOL.map(one, range(0, n, piece)))
+    total = 0
+    for c, a in zip(counts, range(0, n, piece)):
+        total += c
+        if c < min(piece, n - a):                    # end of file inside this piece
+            break
+    return total
+
+
 def iter_dap_text_device(path, device=None, block_bytes: int = 128 << 20, byte_range=None):
     """dap.txt parsed ON THE DEVICE: the file is read in blocks of whole lines into pinned
     memory, the bytes go to the GPU and memo_dap_text_parse turns them into int32 rows (the
@@ -184,9 +225,11 @@ def iter_dap_text_device(path, device=None, block_bytes: int = 128 << 20, byte_r
         view = pin.numpy()
         fh.seek(lo)
         left, carry = hi - lo, 0                       # bytes of the share not read yet; bytes carried over
+        fd, off = fh.fileno(), lo                      # (the block is read by several threads: see _pread_into)
         while left > 0 or carry > 0:
             want = min(left, block_bytes - carry)
-            got = fh.readinto(memoryview(view)[carry:carry + want]) if want > 0 else 0
+            got = _pread_into(fd, memoryview(view)[carry:carry + want], off) if want > 0 else 0
+            off += got
             left -= got
             n = carry + got
             if got == 0 and left > 0:
