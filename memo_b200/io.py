@@ -221,48 +221,67 @@ def iter_dap_text_device(path, device=None, block_bytes: int = 128 << 20, byte_r
             raise MemoError("dap.txt needs a position column and at least one genome column")
         block_bytes = max(int(block_bytes), 4 * len(first) + 64)
         parser = api.DapTextParser(n_fields - 1, block_bytes, device)
-        pin = torch.empty(block_bytes + 64, dtype=torch.uint8, pin_memory=True)
-        view = pin.numpy()
-        fh.seek(lo)
-        left, carry = hi - lo, 0                       # bytes of the share not read yet; bytes carried over
-        fd, off = fh.fileno(), lo                      # (the block is read by several threads: see _pread_into)
-        while left > 0 or carry > 0:
-            want = min(left, block_bytes - carry)
-            got = _pread_into(fd, memoryview(view)[carry:carry + want], off) if want > 0 else 0
-            off += got
-            left -= got
-            n = carry + got
-            if got == 0 and left > 0:
-                left = 0                               # (file shorter than expected)
-            if left == 0:
-                if n and view[n - 1] != 10:            # last line of the share without its newline
-                    view[n] = 10
-                    n += 1
-                cut = n
-            else:
-                # the block ends with its last whole line; the rest opens the next block
-                tail = view[max(0, n - (1 << 16)):n]
-                nl = np.flatnonzero(tail == 10)
-                if nl.size == 0:
-                    nl = np.flatnonzero(view[:n] == 10)
-                    if nl.size == 0:
-                        raise MemoError("dap.txt: a line longer than the text block")
-                    cut = int(nl[-1]) + 1
+        # two pinned blocks: the next one is read (by a helper thread; the read itself fans out,
+        # _pread_into) while the current one is parsed, built and written by the caller
+        pins = [torch.empty(block_bytes + 64, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        views = [p.numpy() for p in pins]
+        from concurrent.futures import ThreadPoolExecutor
+        ahead = ThreadPoolExecutor(1)
+        fd = fh.fileno()
+
+        def read(i, carry, off, want):
+            return _pread_into(fd, memoryview(views[i])[carry:carry + want], off) if want > 0 else 0
+
+        left, carry, off, cur = hi - lo, 0, lo, 0      # bytes of the share not read yet; bytes carried over
+        fut = ahead.submit(read, cur, carry, off, min(left, block_bytes - carry))
+        try:
+            while True:
+                got = fut.result()
+                off += got
+                left -= got
+                n = carry + got
+                if got == 0 and left > 0:
+                    left = 0                           # (file shorter than expected)
+                view = views[cur]
+                if n == 0:
+                    break
+                if left == 0:
+                    if view[n - 1] != 10:              # last line of the share without its newline
+                        view[n] = 10
+                        n += 1
+                    cut = n
                 else:
-                    cut = max(0, n - (1 << 16)) + int(nl[-1]) + 1
-            if cut == 0:
-                break
-            head = bytes(view[:min(cut, 24)])
-            try:
-                pos_first = int(head.split(b" ", 1)[0])
-            except ValueError:
-                raise ValueError("invalid literal for int() in dap.txt") from None
-            rows = parser.parse(pin, cut, pos_first)      # (synchronises: the pinned block is free again)
-            if rows.shape[0]:
-                yield pos_first, rows
-            carry = n - cut
-            if carry:
-                view[:carry] = view[cut:n].copy()
+                    # the block ends with its last whole line; the rest opens the next block
+                    tail = view[max(0, n - (1 << 16)):n]
+                    nl = np.flatnonzero(tail == 10)
+                    if nl.size == 0:
+                        nl = np.flatnonzero(view[:n] == 10)
+                        if nl.size == 0:
+                            raise MemoError("dap.txt: a line longer than the text block")
+                        cut = int(nl[-1]) + 1
+                    else:
+                        cut = max(0, n - (1 << 16)) + int(nl[-1]) + 1
+                if cut == 0:
+                    break
+                head = bytes(view[:min(cut, 24)])
+                try:
+                    pos_first = int(head.split(b" ", 1)[0])
+                except ValueError:
+                    raise ValueError("invalid literal for int() in dap.txt") from None
+                carry = n - cut
+                more = left > 0 or carry > 0
+                if more:
+                    if carry:
+                        views[1 - cur][:carry] = view[cut:n]
+                    fut = ahead.submit(read, 1 - cur, carry, off, min(left, block_bytes - carry))
+                rows = parser.parse(pins[cur], cut, pos_first)    # (synchronises: the pinned block is free again)
+                if rows.shape[0]:
+                    yield pos_first, rows
+                if not more:
+                    break
+                cur = 1 - cur
+        finally:
+            ahead.shutdown(wait=True)                  # (a read still in flight targets the pinned blocks)
 
 
 def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 20, read_bytes: int = 4 << 20):
