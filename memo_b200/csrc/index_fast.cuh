@@ -73,7 +73,8 @@ struct FastParams {
     unsigned int* pool_counter;
     unsigned long long* cursor;        // scratch allocation cursor
     unsigned long long* strip_counter; // wide: next strip to hand out
-    int32_t prefetch;                  // wide: prefetch a strip's next chunk into L2
+    int32_t prefetch;                  // wide: 1 = prefetch a strip's next chunk into L2; 2 = ... with L2 eviction
+                                       // priorities (prefetch evict_last, copy evict_first); 3 = copy evict_first only
     int64_t* result;
 };
 
@@ -116,6 +117,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // the same range on its way into L2 only (no shared-memory destination, no completion)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// ... with L2 eviction priorities: the prefetched lines are kept (evict_last) until the copy that
+// consumes them marks them evict_first
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_prefetch_l2_hint(const void* src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+        : "memory");
 }
 
 

@@ -69,6 +69,7 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
     const unsigned long long lim = (unsigned long long)P.total_bytes & ~15ull;
     const unsigned char* const src = reinterpret_cast<const unsigned char*>(P.dap);
     if (lane == 0) look = atomicAdd(P.strip_counter, 1ull);
+    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
 
     // (per chunk: 32-bit arithmetic on top of the strip's running byte offset)
     auto issue = [&](int s) {
@@ -137,7 +138,8 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
         }
         if (len) {
             mbar_arrive_expect_tx(bar, len);
-            bulk_g2s(data, src + a0, len, bar);
+            if (P.prefetch >= 2) bulk_g2s_hint(data, src + a0, len, bar, pol_first);
+            else bulk_g2s(data, src + a0, len, bar);
         } else {
             mbar_arrive(bar);
         }
@@ -152,7 +154,10 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
             const uint32_t nn = p_left < (uint32_t)T ? p_left : (uint32_t)T;
             const uint32_t h2 = (uint32_t)p_addr & 15u;
             const uint32_t l2 = (h2 + nn * ldb + 15u) & ~15u;
-            if (p_addr - h2 + l2 <= lim) bulk_prefetch_l2(src + (p_addr - h2), l2);
+            if (p_addr - h2 + l2 <= lim) {
+                if (P.prefetch == 2) bulk_prefetch_l2_hint(src + (p_addr - h2), l2, pol_last);
+                else if (P.prefetch == 1) bulk_prefetch_l2(src + (p_addr - h2), l2);
+            }
         }
     };
 
