@@ -48,7 +48,7 @@ if build:
 if query:
     data[f"{tag}_query"] = query[0][1]
     data[f"{tag}_query_duration_under_ncu_ns"] = query[0][2]
-data["_source"] = "ncu captures of round 2 (scripts/gpu_r2_final.sh; --clock-control none), per launch; looked up by bench.py, not measured in its run"
+data["_source"] = "ncu captures of round 2 (scripts/gpu_r2_final2.sh, gpu_r2_final3.sh; --clock-control none), per launch; looked up by bench.py, not measured in its run"
 json.dump(data, open(out, "w"), indent=1)
 for k in (f"{tag}_stream_kernel", f"{tag}_index_build", f"{tag}_query"):
     print(k, data.get(k))
