@@ -822,6 +822,9 @@ def main():
     del wl
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_extras and args.rows == CHR1 and args.cols == 93:
+        # (the 92.6 GB just released keep the memory system busy for a few hundred ms -- a 10-genome
+        #  build started right away runs at 0.71 ms instead of 0.59, scripts/narrow_probe.py)
+        time.sleep(1.0)
         ex_steps = max(5, min(args.steps, 20))
         line["extra_configs"] = [
             extra_config("BASELINE configs[1]: 10 genomes x 100 Mbp, conservation", 100_000_000, 9, False,

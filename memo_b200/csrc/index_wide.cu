@@ -38,7 +38,10 @@ namespace {
 //  note that __launch_bounds__(256, 1) is NOT the same as __launch_bounds__(256): it lets ptxas
 //  take 105 registers and halves the occupancy)
 #ifdef MEMO_WIDE_MIN_CTAS
-#define MEMO_WIDE_BOUNDS __launch_bounds__(256, MEMO_WIDE_MIN_CTAS)
+#ifndef MEMO_WIDE_MAX_THREADS
+#define MEMO_WIDE_MAX_THREADS 256
+#endif
+#define MEMO_WIDE_BOUNDS __launch_bounds__(MEMO_WIDE_MAX_THREADS, MEMO_WIDE_MIN_CTAS)
 #else
 #define MEMO_WIDE_BOUNDS __launch_bounds__(256)
 #endif
@@ -350,6 +353,19 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
                 for (int k = 0; k < KPL; ++k) ra[k] = prv[k];
                 // a row against the one before: true if some cell moved (warp vote)
                 auto moved = [&](const uint32_t* rowp, const uint32_t (&before)[KPL], uint32_t (&row)[KPL]) {
+#ifndef MEMO_SCAN_OR
+                    // (row - before == -1 in every cell of an unchanged row: differences ANDed, one
+                    //  compare; the subtraction can go to the FMA pipe, the integer ALU runs at half rate)
+                    uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) row[k] = rowp[32 * k];
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) {
+                        const uint32_t dd = row[k] - before[k];
+                        acc &= (k == KPL - 1) ? (dd | ~vm[k]) : dd;
+                    }
+                    return __any_sync(FULL, acc != 0xFFFFFFFFu) != 0;
+#else               // (experiment knob: row + 1 - before ORed, three-input adds on the integer ALU)
                     uint32_t acc = 0;
 #pragma unroll
                     for (int k = 0; k < KPL; ++k) row[k] = rowp[32 * k];
@@ -359,6 +375,7 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
                         acc |= (k == KPL - 1) ? (dd & vm[k]) : dd;
                     }
                     return __any_sync(FULL, acc != 0u) != 0;
+#endif
                 };
                 // (leaves the loop with left > 0 and lp at a row that moved something, or left == 0)
                 while (left >= 2) {
