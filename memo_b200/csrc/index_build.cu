@@ -15,7 +15,7 @@
 //   but its predecessor, and rows with E[r] == E[r-1] (the vast majority: E
 //   only moves where a new MEM starts) emit nothing.
 //
-// Three kernels per build:
+// Four kernels per build (0: prep_kernel, the record runs as kernel parameters + cleared control words):
 //  1 a streaming kernel reads the DAP exactly once (bulk async copies into
 //    per-warp shared-memory rings; warps never wait for each other) and appends
 //    the index rows of its work units to a scratch area, unordered:
@@ -27,8 +27,9 @@
 //  2 tile_scan_kernel   block sums of the unit counts; the last block to finish
 //    scans the block sums.
 //  3 strip_gather_kernel   exclusive scan inside each block
-//    of units and copy of every unit's rows from the scratch area to their place
-//    in the ordered output (the extra traffic is 24 B per index row, a few % of
+//    of units and copy of every unit's rows (8-byte scratch rows: MEM end, row
+//    number within the unit << 16 | order) from the scratch area to their place
+//    in the ordered output (the extra traffic is 16 B per index row, a few % of
 //    the DAP).
 // If the input is irregular the result must be discarded and the general build
 // (index_general.cu) run instead; memo_index_build reports that in

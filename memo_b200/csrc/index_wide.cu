@@ -12,20 +12,24 @@
 // The reference sorts every row (:89-90).  Here a row is never sorted: a warp
 // walks a strip of R consecutive rows and keeps A, the sorted MEM ends of the
 // previous row, in registers (lane l holds positions l*KPL .. l*KPL+KPL-1).  E
-// only moves where a new MEM starts, so for most rows nothing changes (one
-// compare per cell), and a cell whose MEM end moves from x to y > x is a
-// delete/insert in A: with i_new = #{A > y} and i_old = #{A >= x} - 1 the
-// positions i_new..i_old shift down by one and y lands at i_new -- two warp
-// reductions and one shuffle instead of a sort.  The index rows of the row are
-// the positions where A changed.  A is sorted from scratch once per strip.
+// only moves where a new MEM starts, so for most rows nothing changes: the row
+// loop only loads a row, compares it with the one before and votes (14 warp
+// instructions per row at KPL = 3).  A row that moved something is handled
+// outside that loop: a cell whose MEM end moves from x to y > x is a
+// delete/insert in A -- the positions holding x <= A <= y shift down by one and
+// y lands on the first of them, one shuffle, a min and a select per slot
+// instead of a sort.  The index rows of the row are the positions where A
+// changed.  A is sorted from scratch once per strip.
 //
 // Strips are handed out by an atomic counter (one per R rows).  A strip streams
-// through the warp's private shared-memory ring in chunks of T rows (bulk async
-// copies + mbarriers, several chunks in flight), so a warp never waits for
-// another warp.  Index rows go straight to the scratch area: a warp reserves
-// P.chunk rows at a time (one atomicAdd) and appends to them, so a strip's output
-// is one block of consecutive scratch rows, or a short chain of blocks when it
-// crosses into the warp's next chunk.  tile_scan_kernel / strip_gather_kernel
+// through the warp's private shared-memory stage in chunks of T rows (bulk async
+// copies + mbarriers; the strip's next chunk is prefetched into L2 with
+// evict_last priority, the copy that consumes it marks the lines evict_first),
+// so a warp never waits for another warp.  Index rows go straight to the
+// scratch area as 8-byte rows {end, row << 16 | order}: a warp reserves P.chunk
+// rows at a time (one atomicAdd) and appends to them, so a strip's output is one
+// block of consecutive scratch rows, or a short chain of blocks when it crosses
+// into the warp's next chunk.  tile_scan_kernel / strip_gather_kernel
 // (index_build.cu) copy the blocks into the ordered output.
 #include "index_fast.cuh"
 #include "warp_sort.cuh"

@@ -337,3 +337,24 @@ def test_stream_kernels_keep_their_register_budget():
             regs[name] = int(m.group(1))
     wide = {k: v for k, v in regs.items() if "wide_kernelILi3E" in k}
     assert len(wide) == 2 and all(v <= 85 for v in wide.values()), wide
+
+
+def test_pread_into_reads_ranges_with_and_without_threads(tmp_path):
+    """io._pread_into (the dap.txt block reader): any offset / length, the end of the file inside
+    a block, one thread and several."""
+    import os
+    from memo_b200 import io
+    data = np.random.default_rng(0).integers(0, 256, 3_000_001, dtype=np.uint8).tobytes()
+    path = tmp_path / "blob"
+    path.write_bytes(data)
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        for threads in (1, 4):
+            for off, n in ((0, len(data)), (7, 1 << 20), (123, 2_500_000), (2_900_000, 500_000),
+                           (len(data), 100), (0, 0)):
+                buf = bytearray(n)
+                got = io._pread_into(fd, memoryview(buf), off, piece=1 << 18, threads=threads)
+                want = data[off:off + n]
+                assert got == len(want) and bytes(buf[:got]) == want, (threads, off, n)
+    finally:
+        os.close(fd)
