@@ -382,11 +382,12 @@ int make_fast_plan(int64_t rows, int32_t C, int32_t ld, int64_t out_cap, const m
         // Up to 460 compare rows per strip, a whole number of chunks (predecessor row included): the
         // sorted row is built from scratch once per strip (~300 warp instructions; at 115 rows per
         // strip that was 2.6 per row, 4 % of the kernel).  Short inputs keep short strips: every
-        // resident warp (4 x 6 per SM) should see >= 24 strips, or the last strips -- and the dense
+        // resident warp (4 x 6 per SM) should see >= 48 strips, or the last strips -- and the dense
         // first strip of a record, one warp's work -- become the kernel's tail (94 genomes x 10 Mbp:
-        // 0.85 ms with 115-row strips, 1.37 ms with 460).
+        // 0.85 ms with 115-row strips, 1.37 ms with 460; 31 M rows, a shard of chr1 on 8 GPUs:
+        // 2.486 ms with 160 - 230 rows, 2.529 with 460; 62 M rows: 4.84 ms with 300, 4.875 with 460).
         static const long long strip_rows_max = env_int("MEMO_WIDE_STRIP_ROWS", 460);
-        long long strip_rows = rows / ((long long)device_sm_count() * 24 * 24);
+        long long strip_rows = rows / ((long long)device_sm_count() * 24 * 48);
         if (strip_rows < 115) strip_rows = 115;
         if (strip_rows > strip_rows_max) strip_rows = strip_rows_max;
         long long R = (opts && opts->emit_buf_records > 0) ? opts->emit_buf_records
