@@ -633,7 +633,9 @@ int memo_index_build(const int32_t* dap, int64_t rows, int32_t n_cols, int32_t l
     P.unit_next = reinterpret_cast<int32_t*>(ws + plan.off_next);
     P.pool = reinterpret_cast<BlockRec*>(ws + plan.off_pool);
     P.pool_cap = plan.pool_cap;
-    static const int prefetch = env_int("MEMO_WIDE_PREFETCH", 2);   // measured: 0 / 1 / 2 / 3 = 19.19 / 19.09 / 18.84 / 19.50 ms at chr1 x 94
+    // (measured at chr1 x 94, kernel ms: no prefetch 19.19, plain prefetch 19.09, prefetch evict_last +
+    //  copies evict_first 18.84 -- what is built in --, evict_first copies without prefetch 19.50)
+    static const int prefetch = env_int("MEMO_WIDE_PREFETCH", 1) != 0;
     P.prefetch = prefetch;
     unsigned int* done = reinterpret_cast<unsigned int*>(ws + plan.off_ctrl + 64);
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(ws + plan.off_partial);

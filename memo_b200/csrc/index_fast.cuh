@@ -73,8 +73,8 @@ struct FastParams {
     unsigned int* pool_counter;
     unsigned long long* cursor;        // scratch allocation cursor
     unsigned long long* strip_counter; // wide: next strip to hand out
-    int32_t prefetch;                  // wide: 1 = prefetch a strip's next chunk into L2; 2 = ... with L2 eviction
-                                       // priorities (prefetch evict_last, copy evict_first); 3 = copy evict_first only
+    int32_t prefetch;                  // wide: prefetch a strip's next chunk into L2 (evict_last; the copies are
+                                       // evict_first either way)
     int64_t* result;
 };
 

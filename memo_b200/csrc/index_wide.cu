@@ -145,8 +145,7 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
         }
         if (len) {
             mbar_arrive_expect_tx(bar, len);
-            if (P.prefetch >= 2) bulk_g2s_hint(data, src + a0, len, bar, pol_first);
-            else bulk_g2s(data, src + a0, len, bar);
+            bulk_g2s_hint(data, src + a0, len, bar, pol_first);
         } else {
             mbar_arrive(bar);
         }
@@ -161,10 +160,7 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
             const uint32_t nn = p_left < (uint32_t)T ? p_left : (uint32_t)T;
             const uint32_t h2 = (uint32_t)p_addr & 15u;
             const uint32_t l2 = (h2 + nn * ldb + 15u) & ~15u;
-            if (p_addr - h2 + l2 <= lim) {
-                if (P.prefetch == 2) bulk_prefetch_l2_hint(src + (p_addr - h2), l2, pol_last);
-                else if (P.prefetch == 1) bulk_prefetch_l2(src + (p_addr - h2), l2);
-            }
+            if (p_addr - h2 + l2 <= lim) bulk_prefetch_l2_hint(src + (p_addr - h2), l2, pol_last);
         }
     };
 
