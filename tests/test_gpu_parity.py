@@ -667,3 +667,16 @@ def test_cli_bed_text_device_equals_host_formatter(tmp_path, monkeypatch):
         outs[mode] = (tmp_path / f"{mode}.bed").read_bytes()
     assert outs["device"] == outs["host"] and len(outs["device"]) > 0
     assert outs["device"].decode() == mo.format_bed(recs, *mo.index_build(vals, recs, True))
+
+
+@pytest.mark.parametrize("C", [9, 93])
+def test_index_more_record_runs_than_one_prep_launch(C):
+    """150 short records in one buffer: the record runs reach the device as kernel parameters,
+    64 per prep launch (index_build.cu) -- three launches here."""
+    lens = [37 + (i * 13) % 41 for i in range(150)]
+    recs = [(f"r{i}", n) for i, n in enumerate(lens)]
+    vals = np.concatenate([mo.synth_dap(n, C, seed=900 + i, dense=(i % 3 == 0)) for i, n in enumerate(lens)])
+    for order in (True, False):
+        res, got = gpu_index(vals, recs, order)
+        assert not res.general
+        assert_index_equal(got, mo.index_build(vals, recs, order), f"C={C} order={order} 150 records")
