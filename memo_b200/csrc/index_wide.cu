@@ -260,8 +260,9 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
                 for (int kk = KPL - 1; kk >= 0; --kk) {
                     const uint32_t before = kk == 0 ? up : A[kk - 1];
                     const uint32_t old = A[kk];
-                    const bool inr = old >= x && old <= y;
-                    const uint32_t nw = inr ? min(before, y) : old;
+                    // (x <= old <= y ? min(before, y) : old, with one compare: above y the minimum
+                    //  is y < old, inside the range it is >= old because before >= old)
+                    const uint32_t nw = old >= x ? max(old, min(before, y)) : old;
                     em[kk] = nw != old && old >= pos;
                     endv[kk] = old;
                     A[kk] = nw;
@@ -292,7 +293,7 @@ __global__ void MEMO_WIDE_BOUNDS wide_kernel(const FastParams P) {
 #pragma unroll
                         for (int kk = KPL - 1; kk >= 0; --kk) {
                             const uint32_t before = kk == 0 ? up : A[kk - 1];
-                            A[kk] = (A[kk] >= x && A[kk] <= y) ? min(before, y) : A[kk];
+                            A[kk] = A[kk] >= x ? max(A[kk], min(before, y)) : A[kk];
                         }
                     } while (m);
                 }
