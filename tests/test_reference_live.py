@@ -102,6 +102,65 @@ def test_parquet_stage_against_live_reference(tmp_path):
     assert ma.row_group(0).column(1).compression == mb.row_group(0).column(1).compression == "ZSTD"
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_index_edge_shapes_against_live_reference(seed, tmp_path):
+    """Wider shapes than the cases above: records of one row, one column, DAPs that stop inside a
+    record (the chr-end rows still follow the last row, dap_to_bed.py:133-134), values far beyond
+    the record length, rows of zeros and ties -- oracle (numpy) and C port against the script."""
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(8100 + seed)
+    lens = [int(rng.integers(1, 30)) for _ in range(int(rng.integers(1, 5)))]
+    C, L = int(rng.integers(1, 8)), sum(lens)
+    mode = seed % 4
+    if mode == 0:
+        vals = np.concatenate([mo.synth_dap(n, C, seed=int(rng.integers(1, 1 << 30)), dense=True) for n in lens])
+    else:
+        vals = rng.integers(0, (12, 3, 80)[mode - 1], size=(L, C))
+    if rng.random() < 0.4 and L > 1:
+        vals = vals[:int(rng.integers(1, L))]                     # partial DAP
+    vals = vals.astype(np.int64)
+    records = [(f"r{i}", n) for i, n in enumerate(lens)]
+    for order in (True, False):
+        want = _run_reference_index(tmp_path, records, vals, order)
+        assert _bed_text(records, mo.index_build(vals, records, order)) == want, (seed, order)
+        assert _bed_text(records, co.index_build(vals, records, order)) == want, (seed, order, "C port")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_query_edge_windows_against_live_reference(seed, tmp_path):
+    """memo_query.py on a multi-record Parquet index: k from 1 to beyond the window, windows that
+    start anywhere and end beyond the record, indexes of regular and irregular DAPs."""
+    pytest.importorskip("numba")
+    pa = pytest.importorskip("pyarrow")
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(9100 + seed)
+    lens = [int(rng.integers(20, 300)) for _ in range(int(rng.integers(1, 4)))]
+    C, L = int(rng.integers(1, 8)), sum(lens)
+    if seed % 3 == 0:
+        vals = np.concatenate([mo.synth_dap(n, C, seed=int(rng.integers(1, 1 << 30)), dense=True) for n in lens])
+    else:
+        vals = rng.integers(0, (40, 5)[seed % 3 - 1], size=(L, C))
+    records = [(f"r{i}", n) for i, n in enumerate(lens)]
+    membership = bool(seed & 1)
+    rec, s, e, c = mo.index_build(vals.astype(np.int64), records, not membership)
+    table = pa.table({"f0": pa.array([records[r][0] for r in rec], pa.utf8()), "f1": pa.array(s, pa.int64()),
+                      "f2": pa.array(e, pa.int64()), "f3": pa.array(c, pa.int64())})
+    pq_path = tmp_path / "idx.parquet"
+    pq.write_table(table, pq_path, compression="ZSTD")
+    ri = int(rng.integers(0, len(lens)))
+    qs = int(rng.integers(0, lens[ri]))
+    qe = int(rng.integers(qs + 1, lens[ri] + 40))
+    k = (1, 2, 5, 31, 64, 200)[seed]
+    out = tmp_path / "q.txt"
+    argv = [sys.executable, os.path.join(SRC, "memo_query.py"), "-b", str(pq_path), "-r", f"r{ri}:{qs}-{qe}",
+            "-k", str(k), "-n", str(C + 1), "-o", str(out)] + (["-m"] if membership else [])
+    subprocess.run(argv, check=True, capture_output=True, text=True)
+    m = rec == ri
+    got = mo.query(s[m], e[m], c[m], qs, qe, k, C + 1, membership)
+    text = mo.format_membership(got) if membership else mo.format_conservation(got)
+    assert out.read_text() == text, (membership, ri, qs, qe, k)
+
+
 @pytest.mark.parametrize("C,order", [(9, True), (9, False), (40, True)])
 def test_c_port_against_live_reference_at_scale(C, order, tmp_path):
     """The C port (bench.py's cpu_baseline / --impl reference arm) on a synthetic
