@@ -28,6 +28,31 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.memo_abi_version() == 7
 
 
+def test_header_binds_from_plain_c(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (no C++, no torch, no Python) includes
+    include/memo_b200.h, links libmemo_b200.so and calls it.  The struct sizes the Python side
+    pins are checked from the C side too."""
+    import shutil
+    from memo_b200 import _build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    libdir = os.path.dirname(_build.build())
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "memo_b200.h"\n'
+                   "int main(void) {\n"
+                   "    if (sizeof(memo_segment_t) != 32 || sizeof(memo_index_opts_t) != 32) return 2;\n"
+                   "    if (memo_last_error() == NULL) return 3;\n"
+                   '    printf("%d\\n", memo_abi_version());\n'
+                   "    return 0;\n}\n")
+    exe = tmp_path / "c_abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lmemo_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "7"
+
+
 def test_struct_layouts_match_header():
     import ctypes as C
     from memo_b200 import _lib
