@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MEMO_B200_ABI_VERSION 7
+#define MEMO_B200_ABI_VERSION 8
 
 #define MEMO_OK 0
 #define MEMO_ERR_ARG (-1)       /* bad argument */
@@ -232,6 +232,49 @@ size_t memo_dap_text_workspace_bytes(int64_t n_bytes);
 int memo_dap_text_parse(const uint8_t* text, int64_t n_bytes, int32_t n_cols, int64_t pos_first,
                         int32_t* out, int64_t max_rows, int32_t ld, int64_t* result,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* MONI `*.lengths` / `*.lengths.vert` text -> one column of a DAP block, on the HOST (this and
+ * memo_lengths_block_parse are the only entry points that do no device work: the tokenizer of the
+ * `--lengths` ingest; the block they fill is what goes to the device).
+ * Replaces src/index.sh:79 (`grep -v '^>' | tr ' ' '\n' | grep .`), the `paste | nl` of
+ * index.sh:83 and the re-parse of src/dap_to_bed.py:87 for one per-genome file.
+ *  text         host bytes [n_bytes]: a run of the file, starting where the previous call stopped
+ *  final_block  != 0: the file ends with this run (a number touching the end is complete);
+ *               0: such a number is left for the next call (result[2] stops before it)
+ *  state        in/out, 0 before the first call of a file: 0 = at the start of a line, 1 = inside
+ *               a line, 2 = inside a '>' header line (dropped up to its newline)
+ *  out          host int32: value i of this call goes to out[i * out_stride]
+ *  max_vals     parsing stops before value max_vals + 1
+ *  result       host int64 [3]: [0] values written, [1] error bits: 1 = a byte that is no digit,
+ *               no white space and no '>' at the start of a line (int() raises in the
+ *               reference), 8 = value >= 2^31; [2] bytes consumed
+ * One thread per call, no shared state: the host parses the files of a block side by side. */
+int memo_lengths_text_parse(const uint8_t* text, int64_t n_bytes, int32_t final_block,
+                            int32_t* state, int32_t* out, int64_t out_stride, int64_t max_vals,
+                            int64_t* result);
+
+/* A per-genome file of the --lengths ingest as memo_lengths_block_parse walks it: the caller opens
+ * the file, owns the buffer (cap bytes) and zeroes everything else before the first call. */
+typedef struct {
+    int32_t fd;        /* open file descriptor, read with read(2) */
+    int32_t state;     /* tokenizer state (memo_lengths_text_parse) */
+    int32_t eof;       /* read(2) returned 0 */
+    int32_t ended;     /* a tile came back short: the file has no lengths left */
+    uint8_t* buf;      /* host buffer */
+    int64_t cap;       /* its size; numbers longer than this are errors */
+    int64_t lo, hi;    /* unparsed bytes buf[lo, hi) */
+    int64_t count;     /* lengths delivered so far */
+    int64_t error;     /* 0, or the error bits of memo_lengths_text_parse; 32 = read(2) failed */
+} memo_lengths_file_t;
+
+/* One block of the --lengths ingest for a group of neighbouring columns, on the HOST: the next
+ * `rows` lengths of files[j] go to out[r * out_stride + j], r = 0 .. rows - 1 (fewer where a file
+ * ends: files[j].count tells).  The block is walked in tiles of tile_rows rows, every file of the
+ * group filling its column of a tile before the next tile starts, so the tile's cache lines are
+ * written while they are resident.  Returns MEMO_ERR_ARG when a file could not be parsed
+ * (files[j].error).  One thread per call; calls on disjoint groups run side by side. */
+int memo_lengths_block_parse(memo_lengths_file_t* files, int32_t n_files, int32_t* out,
+                             int64_t out_stride, int64_t rows, int64_t tile_rows);
 
 /* `memo view` binning.  Replaces src/plot_conservation.py preprocess_data :46-58: per
  * position bin, the number of positions holding each conservation value 0 .. n_docs.

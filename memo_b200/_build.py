@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmemo_b200.so")
-SOURCES = ["abi.cu", "index_build.cu", "index_narrow.cu", "index_wide.cu", "index_wide2.cu", "index_general.cu", "query.cu", "query_planes.cu", "synth.cu", "format.cu", "view.cu", "dap_text.cu"]
+SOURCES = ["abi.cu", "index_build.cu", "index_narrow.cu", "index_wide.cu", "index_wide2.cu", "index_general.cu", "query.cu", "query_planes.cu", "synth.cu", "format.cu", "view.cu", "dap_text.cu", "lengths_text.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-cudart", "static",

@@ -30,6 +30,13 @@ class IndexOpts(C.Structure):
                 ("kernel_variant", C.c_int32), ("reserved", C.c_int32)]
 
 
+class LengthsFile(C.Structure):
+    """memo_lengths_file_t"""
+    _fields_ = [("fd", C.c_int32), ("state", C.c_int32), ("eof", C.c_int32), ("ended", C.c_int32),
+                ("buf", C.c_void_p), ("cap", C.c_int64), ("lo", C.c_int64), ("hi", C.c_int64),
+                ("count", C.c_int64), ("error", C.c_int64)]
+
+
 # symbol -> (restype, argtypes); must list every function include/memo_b200.h declares
 _vp, _i32, _i64, _sz, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_uint64
 SIGNATURES = {
@@ -63,6 +70,9 @@ SIGNATURES = {
     "memo_format_membership": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "memo_dap_text_workspace_bytes": (_sz, [_i64]),
     "memo_dap_text_parse": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "memo_lengths_text_parse": (C.c_int, [_vp, _i64, _i32, C.POINTER(C.c_int32), _vp, _i64, _i64,
+                                          C.POINTER(C.c_int64)]),
+    "memo_lengths_block_parse": (C.c_int, [C.POINTER(LengthsFile), _i32, _vp, _i64, _i64, _i64]),
     "memo_view_bins": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 

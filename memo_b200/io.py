@@ -18,8 +18,6 @@ import pyarrow.parquet as pq
 
 from ._lib import MemoError
 
-_NOT_LENGTHS = re.compile(rb"[^0-9\s]")
-
 INDEX_SCHEMA = pa.schema([("f0", pa.utf8()), ("f1", pa.int64()), ("f2", pa.int64()), ("f3", pa.int64())])
 
 
@@ -284,105 +282,102 @@ def iter_dap_text_device(path, device=None, block_bytes: int = 128 << 20, byte_r
             ahead.shutdown(wait=True)                  # (a read still in flight targets the pinned blocks)
 
 
-def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 20, read_bytes: int = 4 << 20):
+def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 18, read_bytes: int = 1 << 20,
+                         threads: int = 0, tile_rows: int = 2048):
     """Per-genome MONI `*.lengths` / `*.lengths.vert` files streamed side by side: yields int32
-    [n, C] blocks of consecutive pivot positions (all files advance together; memory use is
-    O(C * block)).  Same semantics as read_lengths_columns."""
+    [n, C] blocks of consecutive pivot positions, column j from paths[j] (genome_list.txt order
+    minus the pivot).  Replaces index.sh:79-83 (`grep -v '^>' | tr ' ' '\n' | grep .`,
+    `paste | nl`) and the text re-parse of dap.txt (src/dap_to_bed.py:87): lines that start with
+    '>' are headers, everything else is white-space separated lengths; row i of the stream is
+    pivot position i of the concatenated records.  Memory is O(C * block): all files advance
+    together.  The files are tokenized by `threads` host threads (default: MEMO_LENGTHS_THREADS
+    or up to 16) inside libmemo_b200.so (memo_lengths_block_parse: host code, the GIL is
+    released), each owning a group of neighbouring columns and walking the block in tiles of
+    `tile_rows` rows; the next block is parsed while the caller works on the current one, so a
+    yielded block is valid until the block after it is requested."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from . import _lib
     if not paths:
         raise MemoError("at least one .lengths file is needed")
-
-    class _Col:
-        def __init__(self, path):
-            self.path, self.fh, self.tail, self.vals, self.done = path, open(path, "rb"), b"", [], False
-            self.have = 0
-
-        def fill(self, want):
-            while self.have < want and not self.done:
-                data = self.fh.read(read_bytes)
-                if not data:
-                    self.done = True
-                    data, self.tail = self.tail + b"\n", b""
-                else:
-                    data = self.tail + data
-                    cut = max(data.rfind(b"\n"), data.rfind(b" "))
-                    data, self.tail = data[:cut + 1], data[cut + 1:]
-                if b">" in data:
-                    data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b">"))
-                if _NOT_LENGTHS.search(data):
-                    raise ValueError(f"invalid literal for int() in {self.path}")
-                if not data.strip():
-                    continue
-                with warnings.catch_warnings():
-                    warnings.simplefilter("ignore", DeprecationWarning)
-                    v = np.fromstring(data.decode("ascii"), dtype=np.int64, sep=" ")
-                if v.size:
-                    if v.min() < 0 or v.max() > 2**31 - 1:
-                        raise MemoError("DAP lengths must be in [0, 2^31)")
-                    self.vals.append(v.astype(np.int32))
-                    self.have += v.size
-
-        def take(self, n):
-            buf = np.concatenate(self.vals) if len(self.vals) != 1 else self.vals[0]
-            out, rest = buf[:n], buf[n:]
-            self.vals, self.have = ([rest] if rest.size else []), rest.size
-            return out
-
-    cols = [_Col(p) for p in paths]
+    lib = _lib.load()
+    n_cols = len(paths)
+    if threads <= 0:
+        threads = int(_os.environ.get("MEMO_LENGTHS_THREADS", 0)) or min(16, _os.cpu_count() or 1)
+    threads = max(1, min(threads, n_cols))
+    cuts = [k * n_cols // threads for k in range(threads + 1)]
+    files = (_lib.LengthsFile * n_cols)()
+    bufs_in = []                                                 # keeps the read buffers alive
+    pool = ThreadPoolExecutor(threads)
+    ahead = ThreadPoolExecutor(1)
+    fut = None
     try:
+        for j, p in enumerate(paths):
+            files[j].fd = -1
+        for j, p in enumerate(paths):
+            buf = (C.c_uint8 * read_bytes)()
+            bufs_in.append(buf)
+            files[j].buf = C.cast(buf, C.c_void_p)
+            files[j].cap = read_bytes
+            files[j].fd = _os.open(p, _os.O_RDONLY)
+
+        def fill(k, base):
+            a, b = cuts[k], cuts[k + 1]
+            group = C.cast(C.byref(files, a * C.sizeof(_lib.LengthsFile)), C.POINTER(_lib.LengthsFile))
+            return lib.memo_lengths_block_parse(group, b - a, base + 4 * a, n_cols, block_rows, tile_rows)
+
+        def produce(out):
+            first = files[0].count
+            base = out.ctypes.data
+            list(pool.map(lambda k: fill(k, base), range(threads)))
+            for j, p in enumerate(paths):
+                err = files[j].error
+                if err & 8:
+                    raise MemoError("DAP lengths must be in [0, 2^31)")
+                if err & 32:
+                    raise OSError(f"reading {p} failed")
+                if err:                                          # int() raises in the reference
+                    raise ValueError(f"invalid literal for int() in {p}")
+            for j, p in enumerate(paths):
+                if files[j].count != files[0].count:
+                    which = "fewer" if files[j].count < files[0].count else "more"
+                    raise MemoError(f"{p}: {which} lengths than {paths[0]}, expected the same number "
+                                    "(one per pivot position)")
+            return files[0].count - first
+
+        bufs = [np.empty((block_rows, n_cols), dtype=np.int32) for _ in range(2)]
+        k = 0
+        fut = ahead.submit(produce, bufs[0])
         while True:
-            for c in cols:
-                c.fill(block_rows)
-            n = min(c.have for c in cols)
-            if n == 0:
-                for c in cols:
-                    if c.have:
-                        raise MemoError(f"{c.path}: more lengths than {cols[0].path} (one per pivot position)")
+            n, fut = fut.result(), None
+            out = bufs[k]
+            if n < block_rows:                                    # every file has ended
+                if n:
+                    yield out[:n]
                 return
-            n = min(n, block_rows)
-            out = np.empty((n, len(cols)), dtype=np.int32)
-            for j, c in enumerate(cols):
-                out[:, j] = c.take(n)
+            k = 1 - k
+            fut = ahead.submit(produce, bufs[k])
             yield out
     finally:
-        for c in cols:
-            c.fh.close()
+        if fut is not None:
+            try:
+                fut.result()
+            except Exception:
+                pass
+        ahead.shutdown(wait=True)
+        pool.shutdown(wait=True)
+        for j in range(n_cols):
+            if files[j].fd >= 0:
+                _os.close(files[j].fd)
+                files[j].fd = -1
 
 
-def read_lengths_columns(paths: Sequence[str], threads: int = 8) -> np.ndarray:
-    """Per-genome MONI `*.lengths` (or the `*.lengths.vert` index.sh:79 makes of them) ->
-    int32 [L, C] DAP matrix, one column per file in the order given (genome_list.txt
-    order minus the pivot).  Replaces index.sh:79-83 (`grep -v '^>' | tr ' ' '\n'`,
-    `paste | nl`) and the text re-parse of dap.txt (src/dap_to_bed.py:87): header lines
-    start with '>', every other line holds whitespace-separated lengths; row i of the
-    result is pivot position i of the concatenated records."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    def one(path):
-        with open(path, "rb") as fh:
-            data = fh.read()
-        if b">" in data:
-            data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b">"))
-        if _NOT_LENGTHS.search(data):                            # int() in the reference
-            raise ValueError(f"invalid literal for int() in {path}")
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", DeprecationWarning)
-            col = np.fromstring(data.decode("ascii"), dtype=np.int64, sep=" ")     # any whitespace separates
-        if col.size and (col.min() < 0 or col.max() > 2**31 - 1):
-            raise MemoError("DAP lengths must be in [0, 2^31)")
-        return col.astype(np.int32)
-
-    if not paths:
-        raise MemoError("at least one .lengths file is needed")
-    with ThreadPoolExecutor(max(1, min(threads, len(paths)))) as ex:
-        cols = list(ex.map(one, paths))
-    L = cols[0].size
-    for path, col in zip(paths, cols):
-        if col.size != L:
-            raise MemoError(f"{path}: {col.size} lengths, expected {L} (one per pivot position)")
-    out = np.empty((L, len(cols)), dtype=np.int32)
-    for j, col in enumerate(cols):
-        out[:, j] = col
-    return out
+def read_lengths_columns(paths: Sequence[str], threads: int = 0) -> np.ndarray:
+    """The whole int32 [L, C] DAP matrix of per-genome MONI files (iter_lengths_columns in one piece)."""
+    blocks = [b.copy() for b in iter_lengths_columns(paths, threads=threads)]
+    if not blocks:
+        return np.empty((0, len(paths)), dtype=np.int32)
+    return blocks[0] if len(blocks) == 1 else np.concatenate(blocks)
 
 
 def index_table(records: Sequence[Tuple[str, int]], rec_idx, start, end, order) -> pa.Table:

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in memo_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.memo_abi_version() == 7
+    assert lib.memo_abi_version() == 8
 
 
 def test_header_binds_from_plain_c(tmp_path):
@@ -50,7 +50,7 @@ def test_header_binds_from_plain_c(tmp_path):
                     str(src), "-L", libdir, "-lmemo_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
                    check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
-    assert out.strip() == "7"
+    assert out.strip() == "8"
 
 
 def test_struct_layouts_match_header():
@@ -135,6 +135,129 @@ def test_lengths_ingest_equals_dap_text(example_golden, tmp_path):
     bad.write_text("1 x 3\n")
     with pytest.raises(ValueError):
         io.read_lengths_columns([str(bad)])
+
+
+def _lengths_reference(text):
+    """index.sh:79 (`grep -v '^>' | tr ' ' '\\n' | grep .`) + int() of dap_to_bed.py:87 on one file."""
+    vals = []
+    for line in text.split(b"\n"):
+        if line.startswith(b">"):
+            continue
+        for tok in line.split():
+            if not tok.isdigit():
+                return vals, 1
+            if int(tok) >= 2 ** 31:
+                return vals, 8
+            vals.append(int(tok))
+    return vals, 0
+
+
+def test_lengths_tokenizer_fuzz():
+    """memo_lengths_text_parse (host code of the library) fed random runs of random text, random
+    value budgets and strides, against the shell pipeline's semantics: numbers of 1 .. 10 digits
+    and leading zeros, every kind of white space, headers (with digits, spaces and '>' inside)
+    anywhere, bytes int() rejects, values >= 2^31, numbers cut by the end of a run."""
+    import ctypes as C
+    import random
+    from memo_b200 import _lib
+    lib = _lib.load()
+    rng = random.Random(20241018)
+
+    def run(text, stride):
+        n, vals, pos, hi = len(text), [], 0, 0
+        st, res = C.c_int32(0), (C.c_int64 * 3)()
+        buf = (C.c_uint8 * (n + 1)).from_buffer_copy(text + b"\0")
+        while True:
+            if hi < n:
+                hi = min(n, hi + rng.choice([1, 3, 17, 64, 100, 257, 5000]))
+            final = int(hi == n)
+            want = rng.choice([0, 1, 2, 5, 50, 1000, 3000])
+            out = np.full((max(want, 1), stride), -7, dtype=np.int32)
+            assert lib.memo_lengths_text_parse(C.addressof(buf) + pos, hi - pos, final, st, out.ctypes.data,
+                                               stride, want, res) == 0
+            k, err, used = res
+            assert 0 <= used <= hi - pos and k <= want
+            vals.extend(out[:k, 0].tolist())
+            assert (out[:, 1:] == -7).all() and (out[k:] == -7).all()        # nothing but the column is written
+            pos += used
+            if err:
+                return vals, err
+            if final and pos == n:
+                return vals, 0
+
+    def text(bad):
+        parts = []
+        for _ in range(rng.randint(0, 300)):
+            r = rng.random()
+            if r < 0.03:
+                parts.append(b"\n>" + bytes(rng.choice(b"abc 123>\t") for _ in range(rng.randint(0, 90))) + b"\n")
+            elif r < 0.05 and bad:
+                parts.append(rng.choice([b"x", b"-", b"+", b"1.5", b" >", b"\x00", b"\xff", b":", b"/"]))
+            elif r < 0.06 and bad:
+                parts.append(str(rng.choice([2 ** 31, 2 ** 31 + 5, 10 ** 12, 10 ** 25, 10 ** 70])).encode())
+            else:
+                v = min(rng.randint(0, 10 ** rng.choice([1, 1, 2, 2, 2, 3, 4, 5, 7, 8, 9, 10]) - 1), 2 ** 31 - 1)
+                parts.append((b"0" * rng.randint(1, 12) if rng.random() < 0.05 else b"") + str(v).encode())
+            parts.append(rng.choice([b" ", b" ", b" ", b"\n", b"\n", b"  ", b"\t", b"\r\n", b" \n ", b"\n\n", b" " * 70]))
+        t = b"".join(parts)
+        if rng.random() < 0.3:
+            t = t.rstrip()
+        return (b">hdr 1 2 3\n" if rng.random() < 0.2 else b"") + t
+
+    n_err = 0
+    for it in range(1500):
+        t = text(bad=it % 4 == 0)
+        want, werr = _lengths_reference(t)
+        got, gerr = run(t, rng.choice([1, 1, 3, 93]))
+        if werr or gerr:
+            n_err += 1
+            assert bool(werr) == bool(gerr), (t, werr, gerr)
+        else:
+            assert got == want, t
+    assert n_err > 20
+
+
+def test_lengths_stream_blocks_threads_and_errors(tmp_path):
+    """iter_lengths_columns: the same matrix whatever the block size, read buffer, tile and
+    thread count; ragged, invalid and out-of-range files raise; a closed stream leaves no file open."""
+    from memo_b200 import io
+    from memo_b200._lib import MemoError
+    rng = np.random.default_rng(77)
+    L, C = 5000, 11
+    vals = rng.integers(0, 3000, size=(L, C)).astype(np.int32)
+    vals[rng.random((L, C)) < 0.01] = 2 ** 31 - 1
+    paths = _write_lengths(tmp_path, vals)
+    with open(paths[3], "rb+") as fh:                              # no newline at the end of one file
+        fh.seek(-1, os.SEEK_END)
+        fh.truncate()
+    for kw in (dict(), dict(block_rows=7), dict(block_rows=1000, read_bytes=64, tile_rows=13, threads=3),
+               dict(block_rows=L, threads=1), dict(block_rows=L - 1, read_bytes=4096, threads=32)):
+        got = np.concatenate([b.copy() for b in io.iter_lengths_columns(paths, **kw)])
+        assert got.dtype == np.int32 and np.array_equal(got, vals), kw
+    assert np.array_equal(io.read_lengths_columns(paths), vals)
+    empty = tmp_path / "empty.lengths"
+    empty.write_text(">only a header\n\n  \n")
+    assert io.read_lengths_columns([str(empty)]).shape == (0, 1)
+    assert list(io.iter_lengths_columns([str(empty), str(empty)])) == []
+    short = tmp_path / "short.lengths"
+    short.write_text(">r\n" + " ".join(map(str, vals[:L - 1, 0])) + "\n")
+    for pair in ([paths[0], str(short)], [str(short), paths[0]]):
+        with pytest.raises(MemoError, match="expected the same number"):
+            list(io.iter_lengths_columns(pair, block_rows=512))
+    for text, exc in (("1 2 x 4\n", ValueError), ("1 -2 3\n", ValueError), ("5 >6\n", ValueError),
+                      ("1 2147483648 3\n", MemoError), ("1 " + "9" * 80 + "\n", MemoError)):
+        bad = tmp_path / "bad.lengths"
+        bad.write_text(text)
+        with pytest.raises(exc):
+            io.read_lengths_columns([str(bad)])
+    with pytest.raises(ValueError):                                # a "number" longer than the read buffer
+        bad.write_text("7 " + "1" * 300 + " 8\n")
+        list(io.iter_lengths_columns([str(bad)], read_bytes=128))
+    n_open = len(os.listdir("/proc/self/fd"))
+    it = io.iter_lengths_columns(paths, block_rows=100)
+    next(it)
+    it.close()
+    assert len(os.listdir("/proc/self/fd")) == n_open
 
 
 def test_parquet_compress_bed_cli(example_golden, tmp_path):
