@@ -13,7 +13,6 @@ import numpy as np
 import pyarrow as pa
 import pyarrow.compute as pc
 import pyarrow.csv as pacsv
-import pyarrow.dataset as pads
 import pyarrow.parquet as pq
 
 from ._lib import MemoError
@@ -429,7 +428,8 @@ class IndexParquetWriter:
         """Rows in index order (any batch size)."""
         if table.num_rows == 0:
             return
-        table = table.cast(INDEX_SCHEMA)
+        if not table.schema.equals(INDEX_SCHEMA):
+            table = table.cast(INDEX_SCHEMA)
         f0 = table.column("f0").combine_chunks()
         # cut the batch where the record changes
         change = pc.not_equal(f0.slice(1), f0.slice(0, len(f0) - 1)).to_numpy(zero_copy_only=False)
@@ -451,7 +451,7 @@ class IndexParquetWriter:
 
     def _flush(self) -> None:
         if self.n_pending:
-            t = pa.concat_tables(self.pending).combine_chunks()
+            t = pa.concat_tables(self.pending)
             self.writer.write_table(t, row_group_size=t.num_rows)
             self.n_rows += t.num_rows
         self.pending, self.n_pending = [], 0

@@ -462,6 +462,36 @@ def test_parquet_compress_bed_empty_bed_raises_like_the_reference(tmp_path):
         parquet_compress_bed.bed_to_parquet(str(bed), str(tmp_path / "e.parquet"))
 
 
+def test_parquet_compress_bed_blocks_are_invisible(tmp_path):
+    """bed_to_parquet parses the BED in blocks on a helper thread: the table is the same for any
+    block size (lines cut by a block, a last line without line end, one block, blocks smaller than
+    a line), malformed rows raise in the caller's thread, and nothing is left running."""
+    import threading
+    from memo_b200 import io, parquet_compress_bed as pcb
+    rng = np.random.default_rng(11)
+    lines = []
+    for name, n in (("chr1", 4000), ("a_rather_long_record_name_" * 4, 50), ("chrX", 2500)):
+        f1 = np.sort(rng.integers(0, 10 ** 9, n))
+        lines += [f"{name}\t{a}\t{a + d}\t{o}" for a, d, o in zip(f1, rng.integers(0, 10 ** 5, n), rng.integers(1, 94, n))]
+    text = "\n".join(lines)                                        # no line end after the last row
+    bed = tmp_path / "x.bed"
+    bed.write_text(text)
+    want = [ln.split("\t") for ln in lines]
+    for block in (500_000_000, 4096, 100, 7):
+        out = tmp_path / f"x{block}.parquet"
+        pcb.bed_to_parquet(str(bed), str(out), block_size=block, rows_per_group=1000)
+        t = pq.read_table(out)
+        assert t.schema.equals(io.INDEX_SCHEMA) and t.schema.metadata is None
+        assert t.column("f0").to_pylist() == [w[0] for w in want], block
+        for j in (1, 2, 3):
+            assert t.column(f"f{j}").to_pylist() == [int(w[j]) for w in want], block
+    bad = tmp_path / "bad.bed"
+    bad.write_text("\n".join(lines[:2000]) + "\nchr1\tx\t5\t1\n" + "\n".join(lines[2000:]) + "\n")
+    with pytest.raises(Exception, match="(?i)conversion|invalid|CSV"):
+        pcb.bed_to_parquet(str(bad), str(tmp_path / "bad.parquet"), block_size=4096)
+    assert not [th for th in threading.enumerate() if th.name == "memo-bed-parse"]
+
+
 def test_stream_kernels_keep_their_register_budget():
     """Occupancy is part of the design: four CTAs of six warps of the strip
     kernel per SM need <= 85 registers per thread (ptxas settles on 80; `__launch_bounds__(256, 1)`
