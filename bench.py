@@ -532,6 +532,59 @@ def e2e_text_leg(wl, args):
                     "(BASELINE.md 2b)"}
 
 
+def e2e_lengths_leg(wl, args):
+    """the same slice as e2e_text, but from per-genome MONI `.lengths.vert`
+    files (index.sh:79) through `dap_to_bed --lengths` -- no `paste | nl`, no dap.txt.  The files
+    are tokenized by host threads inside the library (memo_lengths_block_parse), the blocks go
+    through the streaming device build.  The BED must equal the one the dap.txt route writes."""
+    import filecmp
+    import tempfile
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    from memo_b200 import dap_to_bed
+    n = min(wl.Lr, args.e2e_text_rows)
+    vals = wl.dap[:n].cpu().numpy()
+    with tempfile.TemporaryDirectory() as d:
+        fai, bed, bed_text, dap = (os.path.join(d, f) for f in ("p.fa.fai", "out.bed", "text.bed", "dap.txt"))
+        paths = []
+        for j in range(wl.C):
+            paths.append(os.path.join(d, f"g{j:03d}.w_rc.lengths.vert"))
+            pacsv.write_csv(pa.table([pa.array(vals[:, j])], names=["v"]), paths[-1],
+                            write_options=pacsv.WriteOptions(include_header=False))
+        with open(fai, "w") as fh:
+            fh.write(f"chrS\t{wl.rec_len}\t6\t{wl.rec_len}\t{wl.rec_len + 1}\n")
+        flags = ["--mem", "--overlap", "--fai", fai] + (["--order"] if wl.order else [])
+        a = dap_to_bed.parse_arguments(flags + ["--out", bed, "--lengths"] + paths)
+        dap_to_bed.check_args(a)
+        dap_to_bed.main(a)
+        t0 = time.perf_counter()
+        dap_to_bed.main(a)
+        dt = time.perf_counter() - t0
+        size = sum(os.path.getsize(p) for p in paths)
+        # the same rows through the dap.txt route, for the comparison of the two BED files
+        m = min(n, 100_000)
+        cols = [pa.array(np.arange(m, dtype=np.int64))] + [pa.array(vals[:m, j]) for j in range(wl.C)]
+        pacsv.write_csv(pa.table(cols, names=[f"f{i}" for i in range(wl.C + 1)]), dap,
+                        write_options=pacsv.WriteOptions(include_header=False, delimiter=" "))
+        small = []
+        for j in range(wl.C):
+            small.append(os.path.join(d, f"s{j:03d}.lengths"))
+            with open(small[-1], "w") as fh:                 # MONI's own layout: header + one line
+                fh.write(">chrS\n" + " ".join(map(str, vals[:m, j].tolist())) + "\n")
+        for argv, out in ((["--dap", dap], bed_text), (["--lengths"] + small, bed)):
+            b = dap_to_bed.parse_arguments(flags + ["--out", out] + argv)
+            dap_to_bed.check_args(b)
+            dap_to_bed.main(b)
+        same = filecmp.cmp(bed, bed_text, shallow=False)
+    return {"value": n / dt, "unit": "bp/s", "rows": n, "seconds": dt, "lengths_bytes": size, "files": wl.C,
+            "text_gbs": size / dt / 1e9, "host_threads": min(16, os.cpu_count() or 1, wl.C),
+            "equals_dap_txt_route": same, "rows_compared": m,
+            "note": "python -m memo_b200.dap_to_bed --lengths on per-genome .lengths.vert files of the same slice, "
+                    "in process, wall clock: files -> host tokenizer threads (memo_lengths_block_parse) -> "
+                    "streaming device build -> BED text; replaces index.sh:79-83 + the dap.txt re-parse"}
+
+
 def cpu_leg(wl, args):
     """C port of the reference algorithm on all host cores over a bounded sample, and
     the GPU rows / query of the same positions compared with it."""
@@ -793,6 +846,10 @@ def main():
     e2e_text = None
     if rank == 0 and world == 1 and not args.no_e2e and not args.membership:
         e2e_text = e2e_text_leg(wl, args)
+        try:
+            e2e_text["from_lengths_files"] = e2e_lengths_leg(wl, args)
+        except Exception as exc:                            # an extra: it must not cost the line
+            e2e_text["from_lengths_files"] = {"error": repr(exc)[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_leg(wl, args)
