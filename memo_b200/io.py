@@ -371,6 +371,30 @@ def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 18, read_b
                 files[j].fd = -1
 
 
+def read_int_text(path) -> np.ndarray:
+    """White-space separated non-negative decimal integers of a text file -> int32 vector (the
+    conservation vector `memo query` writes, one value per line: src/plot_conservation.py:40-49
+    reads it with int(line.strip()) per line).  Tokenized by the library's host tokenizer; anything
+    int() would reject, and a '>' anywhere, raises ValueError."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    with open(path, "rb") as fh:
+        data = fh.read()
+    if b">" in data:
+        raise ValueError(f"invalid literal for int() in {path}")
+    out = np.empty((len(data) + 1) // 2, dtype=np.int32)          # a value and its separator take two bytes
+    state, res = C.c_int32(0), (C.c_int64 * 3)()
+    buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+    rc = lib.memo_lengths_text_parse(C.addressof(buf) if data else None, len(data), 1, state,
+                                     out.ctypes.data, 1, out.size, res)
+    if rc != 0:
+        raise MemoError(f"memo_lengths_text_parse failed (code {rc})")
+    if res[1]:
+        raise ValueError(f"invalid literal for int() in {path}" if res[1] & 1 else f"value out of range in {path}")
+    return out[:res[0]].copy() if res[0] * 4 < out.size else out[:res[0]]
+
+
 def read_lengths_columns(paths: Sequence[str], threads: int = 0) -> np.ndarray:
     """The whole int32 [L, C] DAP matrix of per-genome MONI files (iter_lengths_columns in one piece)."""
     blocks = [b.copy() for b in iter_lengths_columns(paths, threads=threads)]

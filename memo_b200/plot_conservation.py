@@ -39,10 +39,9 @@ def preprocess_data(path, n_docs, n_bins):
     import numpy as np
     import pandas as pd
     import torch
-    with open(path, "rb") as fh:
-        data = fh.read()
-    vals = np.array(data.split(), dtype=np.int64)        # int() per stripped line (:49)
-    if vals.size and (vals.min() < 0 or vals.max() > 65535):
+    from . import io
+    vals = io.read_int_text(path)                        # int() per stripped line (:49)
+    if vals.size and vals.max() > 65535:
         raise ValueError("conservation values out of range")
     if not torch.cuda.is_available():
         from ._lib import MemoError

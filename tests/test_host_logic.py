@@ -260,6 +260,27 @@ def test_lengths_stream_blocks_threads_and_errors(tmp_path):
     assert len(os.listdir("/proc/self/fd")) == n_open
 
 
+def test_read_int_text_reads_a_conservation_vector(tmp_path):
+    """The input of `memo view` (one conservation value per line, memo_query.py:70) as
+    plot_conservation.py:40-49 reads it; what int() rejects raises ValueError."""
+    from memo_b200 import io
+    rng = np.random.default_rng(5)
+    vec = rng.integers(0, 70000, 100_001)
+    p = tmp_path / "cons.txt"
+    for text in ("\n".join(map(str, vec)) + "\n", "\n".join(map(str, vec)), " \n".join(map(str, vec)) + "\r\n"):
+        p.write_text(text)
+        got = io.read_int_text(str(p))
+        assert got.dtype == np.int32 and np.array_equal(got, vec)
+    p.write_text("")
+    assert io.read_int_text(str(p)).size == 0
+    p.write_text("7\n")
+    assert io.read_int_text(str(p)).tolist() == [7]
+    for bad in ("1\n-2\n", "1\nx\n", "1\n>2\n", ">h\n1\n", "99999999999\n", "1.0\n"):
+        p.write_text(bad)
+        with pytest.raises(ValueError):
+            io.read_int_text(str(p))
+
+
 def test_parquet_compress_bed_cli(example_golden, tmp_path):
     bed = tmp_path / "x.bed"
     bed.write_text(example_golden["cons_bed"])
