@@ -114,7 +114,28 @@ def parquet_stage(d, ref, reps):
     if "reference" in cmds:
         a, b = pq.read_table(os.path.join(d, "ref.parquet")), pq.read_table(os.path.join(d, "ours.parquet"))
         res["tables_equal"] = bool(a.equals(b) and a.schema.equals(b.schema, check_metadata=True))
+        res["query_read"] = query_read_stage(d, ref, reps)
     return res
+
+
+def query_read_stage(d, ref, reps):
+    """memo_query.py:19-36 (filter_pq: two predicate scans of the whole Parquet) on the reference's
+    file against io.read_index_rows (row groups pruned by their statistics) on ours: a 300 kbp
+    window of one of the 16 records, k = 31."""
+    import importlib.util
+    from memo_b200 import io
+    spec = importlib.util.spec_from_file_location("ref_memo_query", os.path.join(ref, "src", "memo_query.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rec, qs, qe, k = "chr1_3", 100_000, 400_000, 31
+    t_ref, rows = best(lambda: mod.filter_pq(os.path.join(d, "ref.parquet"), rec, qs, qe + k), reps)
+    stats = {}
+    t_us, cols = best(lambda: io.read_index_rows(os.path.join(d, "ours.parquet"), rec, qs, qe + k, stats), reps)
+    live = rows[rows[:, 0] > qs]                                  # the rows of the live predicate (SURVEY A.3)
+    same = bool(np.array_equal(live[:, 0], cols[0]) and np.array_equal(live[:, 1], cols[1]) and
+                np.array_equal(live[:, 2], cols[2]))
+    return {"window": f"{rec}:{qs}-{qe}", "k": k, "reference_filter_pq_seconds": t_ref, "rows_reference": int(len(rows)),
+            "read_index_rows_seconds": t_us, "rows": int(len(cols[0])), "row_groups": stats, "live_rows_equal": same}
 
 
 def main():
