@@ -328,7 +328,7 @@ def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 18, read_b
         def produce(out):
             first = files[0].count
             base = out.ctypes.data
-            list(pool.map(lambda k: fill(k, base), range(threads)))
+            rcs = list(pool.map(lambda k: fill(k, base), range(threads)))
             for j, p in enumerate(paths):
                 err = files[j].error
                 if err & 8:
@@ -337,6 +337,8 @@ def iter_lengths_columns(paths: Sequence[str], block_rows: int = 1 << 18, read_b
                     raise OSError(f"reading {p} failed")
                 if err:                                          # int() raises in the reference
                     raise ValueError(f"invalid literal for int() in {p}")
+            if any(rcs):
+                raise MemoError(f"memo_lengths_block_parse failed (codes {rcs})")
             for j, p in enumerate(paths):
                 if files[j].count != files[0].count:
                     which = "fewer" if files[j].count < files[0].count else "more"
