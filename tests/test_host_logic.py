@@ -253,11 +253,20 @@ def test_lengths_stream_blocks_threads_and_errors(tmp_path):
     with pytest.raises(ValueError):                                # a "number" longer than the read buffer
         bad.write_text("7 " + "1" * 300 + " 8\n")
         list(io.iter_lengths_columns([str(bad)], read_bytes=128))
-    n_open = len(os.listdir("/proc/self/fd"))
+    def open_lengths_files():
+        out = []
+        for fd in os.listdir("/proc/self/fd"):
+            try:
+                out.append(os.readlink(f"/proc/self/fd/{fd}"))
+            except OSError:
+                pass
+        return [t for t in out if t.startswith(str(tmp_path))]
+
     it = io.iter_lengths_columns(paths, block_rows=100)
     next(it)
+    assert len(open_lengths_files()) == C
     it.close()
-    assert len(os.listdir("/proc/self/fd")) == n_open
+    assert open_lengths_files() == []
 
 
 def test_read_int_text_reads_a_conservation_vector(tmp_path):
