@@ -217,6 +217,36 @@ def test_lengths_tokenizer_fuzz():
     assert n_err > 20
 
 
+def test_lengths_tokenizer_every_alignment():
+    """Numbers of 1 .. 10 digits at every offset of the tokenizer's 64-byte steps, followed by each
+    kind of separator; a number touching the end of a run is left for the next run unless the
+    file ends; a value budget stops in the middle of a step."""
+    import ctypes as C
+    from memo_b200 import _lib
+    lib = _lib.load()
+
+    def parse(text, final=1, want=10 ** 4):
+        out, st, res = np.full(want, -7, dtype=np.int32), C.c_int32(0), (C.c_int64 * 3)()
+        buf = (C.c_uint8 * (len(text) + 1)).from_buffer_copy(text + b"\0")
+        assert lib.memo_lengths_text_parse(C.addressof(buf), len(text), final, st, out.ctypes.data, 1, want, res) == 0
+        assert res[1] == 0
+        return out[:res[0]].tolist(), res[2]
+
+    for offset in range(0, 140, 1):
+        for digits in range(1, 11):
+            for sep in (b" ", b"\n", b"\t "):
+                number = ("9" * digits if digits < 10 else "2147483647").encode()
+                body = b" " * offset + number + sep + b"12 345 6 " * 20
+                for tail in (b"", b"7", b"\n"):
+                    text = body + tail
+                    want = [int(x) for x in text.split()]
+                    assert parse(text) == (want, len(text)), (offset, digits, sep, tail)
+                    got, used = parse(text, final=0)
+                    assert (got, used) == ((want[:-1], len(text) - 1) if tail == b"7" else (want, len(text)))
+                    for budget in (1, 2, 5):
+                        assert parse(text, want=budget)[0] == want[:budget]
+
+
 def test_lengths_stream_blocks_threads_and_errors(tmp_path):
     """iter_lengths_columns: the same matrix whatever the block size, read buffer, tile and
     thread count; ragged, invalid and out-of-range files raise; a closed stream leaves no file open."""
