@@ -128,3 +128,38 @@ def test_view_bins_known_answers():
     import pytest
     with pytest.raises(ZeroDivisionError):
         mo.view_bins([1, 2], 5, 4)
+
+
+def test_k_sweep_planes_follow_from_the_smaller_k():
+    """A property of memo_query.py:42-63 a fused k sweep may rely on: a row paints
+    [f2 - s - (k - 1), f1 - s) clipped to the window, so for k' > k every painted run grows to the
+    left by k' - k and the only other change is rows that paint for the first time.  Per genome /
+    order column:  painted(k') = dilate_left(painted(k), k' - k)  |  rows first non-empty at k'."""
+    rng = np.random.default_rng(4)
+    for case in range(30):
+        L, C = int(rng.integers(200, 1200)), int(rng.integers(1, 9))
+        if case % 3 == 0:
+            vals = mo.synth_dap(L, C, seed=int(rng.integers(1, 1 << 30)), dense=True)
+        else:
+            vals = rng.integers(0, (60, 6)[case % 3 - 1], size=(L, C))
+        _, f1, f2, f3 = mo.index_build(vals.astype(np.int64), [("r", L)], order=bool(case & 1))
+        n_docs = C + 1
+        qs = int(rng.integers(0, L // 2))
+        qe = int(rng.integers(qs + 1, L + 30))
+        W = qe - qs
+        ks = sorted(set(int(x) for x in rng.integers(1, 120, 6)))
+        prev = k_prev = None
+        for k in ks:
+            painted = 1 - mo.query(f1, f2, f3, qs, qe, k, n_docs, True)       # [W, n_docs]: 1 where a row painted
+            if prev is not None:
+                want = prev.copy()
+                for j in range(1, k - k_prev + 1):                            # grow every run to the left
+                    want[:-j] |= prev[j:]
+                m = f1 > qs
+                b = np.clip(f1[m] - qs, 0, W)
+                a_prev, a_now = (np.clip(f2[m] - qs - (kk - 1), 0, W) for kk in (k_prev, k))
+                first = (a_prev >= b) & (a_now < b)                           # rows that paint for the first time
+                for a, e, j in zip(a_now[first], b[first], f3[m][first]):
+                    want[a:e, j] = 1
+                assert np.array_equal(want, painted), (case, k_prev, k)
+            prev, k_prev = painted, k
